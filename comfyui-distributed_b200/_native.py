@@ -1,0 +1,156 @@
+"""ctypes binding of libusdu_b200.so (C ABI declared in include/usdu_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a
+``NativeError`` is raised.  The library is built in-tree by ``__graft_entry__.build()``
+(``make -C comfyui-distributed_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
+
+# constants mirrored from include/usdu_b200.h (checked against the header in tests)
+ABI_VERSION = 1
+TILE_WORDS = 16
+T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
+T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
+T_SUP_X0, T_SUP_Y0, T_SUP_X1, T_SUP_Y1 = 12, 13, 14, 15
+TAB_HEADER = 4
+CROP_ITEM_WORDS = 6
+BLEND_ITEM_WORDS = 4
+COVER_WORDS = 4
+MASK_WORDS = 16
+BLOCK_W = 64
+BLOCK_H = 32
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGNATURES = {
+    "usdu_abi_version": (c_int, []),
+    "usdu_last_error": (c_char_p, []),
+    "usdu_device_count": (c_int, []),
+    "usdu_resample_ksize": (c_int, [c_int, c_int]),
+    "usdu_resample_table_words": (c_int64, [c_int, c_int]),
+    "usdu_build_resample_table": (c_int, [c_int, c_int, POINTER(c_int32)]),
+    "usdu_box_blur_params": (c_int, [c_float, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
+    "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_pack_tiles_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "usdu_unpack_tiles_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "usdu_mask_scratch_bytes": (c_int64, [POINTER(c_int32), c_int]),
+    "usdu_build_feather_masks": (c_int, [POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
+    "usdu_tile_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_void_p, c_void_p]),
+    "usdu_tile_blend": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises NativeError when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C comfyui-distributed_b200/csrc`). "
+            "There is no CPU fallback.")
+    try:
+        h = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise NativeError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(h, name)
+        except AttributeError as e:
+            raise NativeError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    if h.usdu_abi_version() != ABI_VERSION:
+        raise NativeError(f"ABI mismatch: library {h.usdu_abi_version()} != binding {ABI_VERSION}")
+    _lib = h
+    return h
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = lib().usdu_last_error()
+        raise NativeError(f"{what} failed ({status}): {msg.decode() if msg else '?'}")
+
+
+def _i32p(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(POINTER(c_int32))
+
+
+# ---- host-side builders -------------------------------------------------------------
+def build_resample_table(in_size: int, out_size: int) -> np.ndarray:
+    L = lib()
+    words = L.usdu_resample_table_words(in_size, out_size)
+    if words < 0:
+        _check(int(words), "usdu_resample_table_words")
+    tab = np.zeros(int(words), dtype=np.int32)
+    _check(L.usdu_build_resample_table(in_size, out_size, _i32p(tab)), "usdu_build_resample_table")
+    return tab
+
+
+def box_blur_params(radius: float):
+    rad, ww, fw = c_int32(), c_uint32(), c_uint32()
+    _check(lib().usdu_box_blur_params(float(radius), ctypes.byref(rad), ctypes.byref(ww), ctypes.byref(fw)),
+           "usdu_box_blur_params")
+    return rad.value, ww.value, fw.value
+
+
+# ---- device entry points (raw pointers; torch supplies memory and the stream) ----------
+def quantize_canvas(img_ptr, canvas_ptr, B, H, W, pitch, stream):
+    _check(lib().usdu_quantize_canvas(img_ptr, canvas_ptr, B, H, W, pitch, stream), "usdu_quantize_canvas")
+
+
+def dequantize_canvas(canvas_ptr, img_ptr, B, H, W, pitch, stream):
+    _check(lib().usdu_dequantize_canvas(canvas_ptr, img_ptr, B, H, W, pitch, stream), "usdu_dequantize_canvas")
+
+
+def pack_tiles_u8(src_ptr, dst_ptr, n, stream):
+    _check(lib().usdu_pack_tiles_u8(src_ptr, dst_ptr, n, stream), "usdu_pack_tiles_u8")
+
+
+def unpack_tiles_f32(src_ptr, dst_ptr, n, stream):
+    _check(lib().usdu_unpack_tiles_f32(src_ptr, dst_ptr, n, stream), "usdu_unpack_tiles_f32")
+
+
+def mask_scratch_bytes(specs: np.ndarray) -> int:
+    n = lib().usdu_mask_scratch_bytes(_i32p(specs), specs.shape[0])
+    if n < 0:
+        _check(int(n), "usdu_mask_scratch_bytes")
+    return int(n)
+
+
+def build_feather_masks(specs: np.ndarray, pool_ptr, scratch_ptr, stream):
+    _check(lib().usdu_build_feather_masks(_i32p(specs), specs.shape[0], pool_ptr, scratch_ptr, stream),
+           "usdu_build_feather_masks")
+
+
+def tile_crop_resize(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, items_ptr, n_items, patch_w, patch_h,
+                     out_ptr, stream):
+    _check(lib().usdu_tile_crop_resize(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, items_ptr, n_items,
+                                       patch_w, patch_h, out_ptr, stream), "usdu_tile_crop_resize")
+
+
+def tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_ptr, n_items, cover_ptr, patch_w,
+               patch_h, src_ptr, src_is_u8, stream):
+    _check(lib().usdu_tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_ptr, n_items,
+                                 cover_ptr, patch_w, patch_h, src_ptr, int(src_is_u8), stream), "usdu_tile_blend")

@@ -1,0 +1,72 @@
+// usdu_common.cuh -- shared declarations for libusdu_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/usdu_b200.h"
+
+namespace usdu {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow Resample.c PRECISION_BITS
+constexpr int BW = USDU_BLOCK_W;            // canvas / output block, pixels
+constexpr int BH = USDU_BLOCK_H;
+constexpr int kThreads = 256;
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define USDU_REQUIRE(cond, ...)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::usdu::set_error(__VA_ARGS__);          \
+            return USDU_ERR_INVALID;                 \
+        }                                            \
+    } while (0)
+
+#define USDU_CUDA(call)                                              \
+    do {                                                             \
+        int _s = ::usdu::check_cuda((call), #call);                  \
+        if (_s != USDU_OK) return _s;                                \
+    } while (0)
+
+// (uint8)(255.f * x): fp32 multiply (round to nearest), C truncation, wrap to 8 bits.
+// utils/image.py:8-10 -- numpy's float32 -> uint8 cast on x86 (cvttss2si, low byte).
+__device__ __forceinline__ uint32_t quant_u8(float x) {
+    return static_cast<uint32_t>(__float2int_rz(__fmul_rn(255.0f, x))) & 0xFFu;
+}
+
+// u / 255.0f with IEEE division (utils/image.py:13).
+__device__ __forceinline__ float dequant_u8(uint32_t u) {
+    return __fdiv_rn(static_cast<float>(u), 255.0f);
+}
+
+__device__ __forceinline__ uint32_t clip8(int v) {
+    return static_cast<uint32_t>(min(max(v, 0), 255));
+}
+
+// AlphaComposite.c with an opaque destination (see oracle/usdu_oracle.py composite_u8).
+__device__ __forceinline__ uint32_t composite8(uint32_t S, uint32_t D, uint32_t A) {
+    uint32_t tmp = S * (A * 128u) + D * ((255u - A) * 128u) + (0x80u << 7);
+    tmp = ((tmp >> 8) + tmp) >> 8;
+    return tmp >> 7;
+}
+
+struct TableView {
+    int in_size, out_size, ksize;
+    const int32_t* bounds;  // out_size x 2
+    const int32_t* kk;      // out_size x ksize
+};
+
+__device__ __forceinline__ TableView table_at(const int32_t* tabs, int off) {
+    TableView t;
+    const int32_t* p = tabs + off;
+    t.in_size = p[0];
+    t.out_size = p[1];
+    t.ksize = p[2];
+    t.bounds = p + USDU_TAB_HEADER;
+    t.kk = t.bounds + 2 * t.out_size;
+    return t;
+}
+
+}  // namespace usdu

@@ -1,0 +1,149 @@
+// usdu_host.cu -- library plumbing and the host-side table builders.
+//
+// The builders restate Pillow's setup arithmetic with the same C types Pillow uses so
+// the fixed-point tables are bit-identical to what the reference's CPU path gets from
+// Image.resize(..., LANCZOS) (upscale/tile_ops.py:88,148,329) and
+// ImageFilter.GaussianBlur (upscale/tile_ops.py:306):
+//   Resample.c  precompute_coeffs / normalize_coeffs_8bpc  -> usdu_build_resample_table
+//   BoxBlur.c   _gaussian_blur_radius / ImagingHorizontalBoxBlur -> usdu_box_blur_params
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "usdu_common.cuh"
+
+namespace usdu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return USDU_OK;
+    set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return USDU_ERR_CUDA;
+}
+
+}  // namespace usdu
+
+extern "C" {
+
+int usdu_abi_version(void) { return USDU_ABI_VERSION; }
+
+const char* usdu_last_error(void) { return usdu::g_err; }
+
+int usdu_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        usdu::check_cuda(e, "cudaGetDeviceCount");
+        cudaGetLastError();
+        return USDU_ERR_CUDA;
+    }
+    return n;
+}
+
+// ---- LANCZOS tables -------------------------------------------------------------------
+static double sinc_filter(double x) {
+    if (x == 0.0) return 1.0;
+    x = x * M_PI;
+    return sin(x) / x;
+}
+
+static double lanczos_filter(double x) {
+    /* truncated sinc, support 3 */
+    if (-3.0 <= x && x < 3.0) return sinc_filter(x) * sinc_filter(x / 3);
+    return 0.0;
+}
+
+int usdu_resample_ksize(int in_size, int out_size) {
+    if (in_size <= 0 || out_size <= 0) {
+        usdu::set_error("usdu_resample_ksize: sizes must be positive (%d -> %d)", in_size, out_size);
+        return USDU_ERR_INVALID;
+    }
+    double filterscale = (double)in_size / out_size;
+    if (filterscale < 1.0) filterscale = 1.0;
+    double support = 3.0 * filterscale;
+    return (int)ceil(support) * 2 + 1;
+}
+
+int64_t usdu_resample_table_words(int in_size, int out_size) {
+    int ks = usdu_resample_ksize(in_size, out_size);
+    if (ks < 0) return ks;
+    return (int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks);
+}
+
+int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
+    USDU_REQUIRE(table != nullptr, "usdu_build_resample_table: table is null");
+    int ksize = usdu_resample_ksize(in_size, out_size);
+    if (ksize < 0) return ksize;
+    double scale, filterscale;
+    scale = filterscale = (double)in_size / out_size;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 3.0 * filterscale;
+    const double ss = 1.0 / filterscale;
+    table[0] = in_size;
+    table[1] = out_size;
+    table[2] = ksize;
+    table[3] = 0;
+    int32_t* bounds = table + USDU_TAB_HEADER;
+    int32_t* kk = bounds + 2 * (int64_t)out_size;
+    std::vector<double> w(ksize);
+    for (int xx = 0; xx < out_size; xx++) {
+        double center = (xx + 0.5) * scale;
+        double ww = 0.0;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < xmax; x++) {
+            double v = lanczos_filter((x + xmin - center + 0.5) * ss);
+            w[x] = v;
+            ww += v;
+        }
+        int32_t* k = kk + (int64_t)xx * ksize;
+        for (int x = 0; x < xmax; x++) {
+            double v = w[x];
+            if (ww != 0.0) v /= ww;
+            if (v < 0)
+                k[x] = (int)(-0.5 + v * (1 << usdu::kPrecisionBits));
+            else
+                k[x] = (int)(0.5 + v * (1 << usdu::kPrecisionBits));
+        }
+        for (int x = xmax; x < ksize; x++) k[x] = 0;
+        bounds[xx * 2 + 0] = xmin;
+        bounds[xx * 2 + 1] = xmax;
+    }
+    return USDU_OK;
+}
+
+// ---- Gaussian-as-3-box parameters ---------------------------------------------------
+int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw) {
+    USDU_REQUIRE(rad && ww && fw, "usdu_box_blur_params: null output pointer");
+    USDU_REQUIRE(radius > 0.0f, "usdu_box_blur_params: radius must be > 0");
+    const float passes = 3;
+    // volatile keeps every step a rounded C float exactly like BoxBlur.c compiled for x86-64
+    volatile float sigma2 = radius * radius / passes;
+    volatile float L = sqrt(12.0 * sigma2 + 1.0);
+    volatile float l = floor((L - 1.0) / 2.0);
+    volatile float a = (2 * l + 1) * (l * (l + 1) - 3 * sigma2);
+    a = a / (6 * (sigma2 - (l + 1) * (l + 1)));
+    volatile float fr = l + a;
+    int r = (int)fr;
+    uint32_t w = (uint32_t)((uint32_t)(1 << 24) / (fr * 2 + 1));
+    uint32_t f = ((1 << 24) - (r * 2 + 1) * w) / 2;
+    *rad = r;
+    *ww = w;
+    *fw = f;
+    return USDU_OK;
+}
+
+}  // extern "C"

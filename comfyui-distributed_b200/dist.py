@@ -1,0 +1,169 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch; gloo in the CPU tests).  Replaces the reference's HTTP + PNG transport:
+
+* upscale/worker_comms.py:16-108  (PNG multipart POST of processed tiles)  and
+  upscale/result_collector.py:36-182 (master drain loop)   -> all_gather of u8 tiles
+* upscale/worker_comms.py:124-188 (HTTP pull of tile ids)  -> static plan (planner.partition)
+* nodes/collector.py:84-119 + api/job_routes.py:273-343 (base64 PNG per image)
+                                                           -> all_gather of u8 images
+
+Semantics kept (`replay_static`): every participant starts from the
+quantised input, crops from ITS OWN progressive canvas, and the result is the master's
+canvas with every worker tile blended on top in ascending tile id
+(upscale/modes/static.py:521-553).  Workers return their input unchanged (:314).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+def dist_info(group=None) -> Tuple[int, int]:
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(group), td.get_world_size(group)
+    return 0, 1
+
+
+# --------------------------------------------------------------------------------------
+# transport (device agnostic: NCCL on CUDA tensors, gloo on CPU tensors in the tests)
+# --------------------------------------------------------------------------------------
+def all_gather_bytes(payload: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int]]:
+    """All-gather variable-length u8 payloads.  Returns (buffer [world, cap], sizes).
+    One size exchange (int64 all_gather) + one padded all_gather_into_tensor."""
+    assert payload.dtype == torch.uint8 and payload.dim() == 1
+    rank, world = dist_info(group)
+    if world == 1:
+        return payload.view(1, -1), [payload.numel()]
+    n = torch.tensor([payload.numel()], dtype=torch.int64, device=payload.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=payload.device)
+    td.all_gather_into_tensor(sizes, n, group=group)
+    sizes = [int(s) for s in sizes.tolist()]
+    cap = max(max(sizes), 1)
+    cap = (cap + 15) // 16 * 16
+    send = payload
+    if payload.numel() != cap:
+        send = torch.zeros(cap, dtype=torch.uint8, device=payload.device)
+        send[: payload.numel()] = payload
+    out = torch.empty((world, cap), dtype=torch.uint8, device=payload.device)
+    td.all_gather_into_tensor(out.view(-1), send, group=group)
+    return out, sizes
+
+
+def tile_payload_layout(plan, assignment: Sequence[Sequence[int]], B: int):
+    """Byte offset of every tile's u8 [B,ph,pw,3] block inside its owner's payload, in
+    the owner's processing order.  -> ({tile: (rank, offset)}, payload bytes per rank)"""
+    where: Dict[int, Tuple[int, int]] = {}
+    sizes = []
+    for r, tiles in enumerate(assignment):
+        cur = 0
+        for tid in tiles:
+            t = plan.tiles[tid]
+            where[tid] = (r, cur)
+            cur += B * t.ph * t.pw * 3
+            cur = (cur + 15) // 16 * 16
+        sizes.append(cur)
+    return where, sizes
+
+
+def final_blend_order(assignment: Sequence[Sequence[int]]) -> List[int]:
+    """Tile ids of all NON-master participants in the order the master composites them
+    (ascending tile id, upscale/modes/static.py:521-526)."""
+    return sorted(t for r, tiles in enumerate(assignment) if r != 0 for t in tiles)
+
+
+# --------------------------------------------------------------------------------------
+# static mode, SPMD
+# --------------------------------------------------------------------------------------
+def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int,
+                   mask_blur: int, force_uniform_tiles: bool = True, group=None,
+                   assignment: Optional[Sequence[Sequence[int]]] = None, all_ranks_result: bool = False,
+                   stats: Optional[dict] = None) -> torch.Tensor:
+    """Every rank calls this with the same (replicated) CUDA image, like the reference's
+    workers which each re-execute the upstream graph.  Rank 0 returns the
+    blended canvas; other ranks return `image` unchanged unless all_ranks_result."""
+    from . import _native as nat
+    from .engine import Canvas, DevicePlan, _require_cuda, _stream_ptr, run_progressive
+    from .planner import get_plan
+
+    _require_cuda(image, "image")
+    rank, world = dist_info(group)
+    B, H, W, _ = image.shape
+    plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
+    asg = [list(a) for a in (assignment if assignment is not None else plan.partition(world))]
+    if len(asg) != world:
+        raise ValueError(f"assignment has {len(asg)} participants, world size is {world}")
+    with torch.cuda.device(image.device):
+        dp = DevicePlan.get(plan, image.device)
+        canvas = Canvas(dp, B).load(image)
+        base = canvas.clone() if (all_ranks_result and rank != 0) else None
+        shipped = run_progressive(canvas, asg[rank], denoiser, keep_processed=world > 1)
+        if world > 1:
+            where, sizes = tile_payload_layout(plan, asg, B)
+            payload = torch.zeros(sizes[rank], dtype=torch.uint8, device=image.device)
+            for tid in asg[rank]:
+                off = where[tid][1]
+                t = shipped[tid]
+                payload[off: off + t.numel()] = t.reshape(-1)
+            gathered, _ = all_gather_bytes(payload, group)
+            cap = gathered.shape[1]
+            if rank == 0 or all_ranks_result:
+                target = canvas
+                order = final_blend_order(asg)
+                if rank != 0:
+                    # rebuild the master's canvas: base + master tiles in the master's order
+                    target = base
+                    order = list(asg[0]) + order
+                offs = np.array([where[t][0] * cap + where[t][1] for t in order], dtype=np.int64)
+                target.blend(order, gathered.view(-1), offs)
+                canvas = target
+        produce = rank == 0 or all_ranks_result
+        res = canvas.result() if produce else image
+    if stats is not None:
+        stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches
+        stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes
+        stats["tiles"] = len(plan.tiles)
+        stats["tiles_this_rank"] = len(asg[rank])
+        stats["conflict_free"] = plan.conflict_free(asg)
+    return res
+
+
+# --------------------------------------------------------------------------------------
+# collector
+# --------------------------------------------------------------------------------------
+def collector_order(world: int, enabled_worker_ids: Sequence[str], worker_id_of_rank: Sequence[str]) -> List[int]:
+    """Rank order of the collected batch: master (rank 0) first, then workers in the
+    order of `enabled_worker_ids`, then unexpected ids sorted (nodes/collector.py:193-223)."""
+    order = [0]
+    rank_of = {str(w): r for r, w in enumerate(worker_id_of_rank) if r != 0}
+    seen = set()
+    for w in [str(x) for x in enabled_worker_ids]:
+        if w in seen:
+            continue
+        seen.add(w)
+        if w in rank_of:
+            order.append(rank_of[w])
+    for w in sorted(rank_of):
+        if w not in seen:
+            order.append(rank_of[w])
+    return order
+
+
+def gather_image_payloads(payload: torch.Tensor, shape: Sequence[int], group=None):
+    """All-gather one u8 image batch per rank; shapes may differ in the batch dimension.
+    -> list of u8 tensors [B_r, H, W, C] indexed by rank."""
+    rank, world = dist_info(group)
+    meta = torch.tensor(list(shape), dtype=torch.int64, device=payload.device)
+    metas = torch.empty((world, 4), dtype=torch.int64, device=payload.device)
+    if world == 1:
+        metas[0] = meta
+    else:
+        td.all_gather_into_tensor(metas.view(-1), meta, group=group)
+    buf, _ = all_gather_bytes(payload.reshape(-1), group)
+    out = []
+    for r in range(world):
+        b, h, w, c = [int(v) for v in metas[r].tolist()]
+        out.append(buf[r, : b * h * w * c].view(b, h, w, c))
+    return out

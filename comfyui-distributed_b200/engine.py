@@ -1,0 +1,239 @@
+"""Device pipeline of the USDU tile path on one B200: u8 canvas resident in HBM, tiles
+cropped / blended by the sm_100a kernels in libusdu_b200.so, the sampler injected as a
+callable on device tensors.  torch is used for memory, streams and (in dist.py) NCCL.
+
+Replaces upscale/modes/single_gpu.py:8-72 (progressive driver) and the pixel half of
+upscale/modes/static.py (per-participant canvases, sorted final blend :521-553).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .planner import Plan, Tile, WorkList, get_plan
+
+Denoiser = Callable[[torch.Tensor, List[Tile]], torch.Tensor]
+"""denoise(tiles fp32 cuda [n, B, ph, pw, 3] in [0,1], tile rows) -> same shape, fp32.
+The n tiles of one call have pairwise disjoint crop windows (they are independent)."""
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise nat.NativeError(f"{what} must be a CUDA tensor: the USDU kernels have no CPU path")
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DevicePlan:
+    """Plan tables resident on one device (+ the feather templates, built there)."""
+
+    _cache: Dict[tuple, "DevicePlan"] = {}
+
+    def __init__(self, plan: Plan, device: torch.device):
+        self.plan = plan
+        self.device = device
+        self.tiles = torch.from_numpy(plan.tile_desc).to(device)
+        self.tabs = torch.from_numpy(plan.tabs).to(device)
+        self.mask_pool = torch.empty(plan.mask_pool_bytes, dtype=torch.uint8, device=device)
+        scratch = torch.empty(nat.mask_scratch_bytes(plan.mask_specs), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            nat.build_feather_masks(plan.mask_specs, self.mask_pool.data_ptr(), scratch.data_ptr(), _stream_ptr())
+        torch.cuda.current_stream(device).synchronize()   # scratch may be freed now
+        self._wl: Dict[tuple, tuple] = {}
+
+    @classmethod
+    def get(cls, plan: Plan, device: torch.device) -> "DevicePlan":
+        key = (id(plan), device.index)
+        dp = cls._cache.get(key)
+        if dp is None or dp.plan is not plan:
+            if len(cls._cache) > 8:
+                cls._cache.clear()
+            dp = cls._cache[key] = DevicePlan(plan, device)
+        return dp
+
+    def _upload(self, wl: WorkList):
+        items = torch.from_numpy(wl.items).to(self.device)
+        cover = torch.from_numpy(wl.cover).to(self.device) if wl.cover is not None else None
+        return items, cover
+
+    def crop_list(self, tile_ids: Tuple[int, ...], B: int):
+        key = ("crop", tile_ids, B)
+        if key not in self._wl:
+            wl, offs, total = self.plan.crop_worklist(tile_ids, B)
+            self._wl[key] = (wl, offs, total) + self._upload(wl)
+        return self._wl[key]
+
+    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool):
+        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8)
+        if key not in self._wl:
+            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4)
+            self._wl[key] = (wl,) + self._upload(wl)
+        return self._wl[key]
+
+
+class Canvas:
+    """The progressive u8 canvas [B, H, pitch] of one participant."""
+
+    def __init__(self, dplan: DevicePlan, B: int):
+        self.dp = dplan
+        self.plan = dplan.plan
+        self.B = B
+        self.pitch = (self.plan.W * 3 + 127) // 128 * 128
+        self.buf = torch.empty((B, self.plan.H, self.pitch), dtype=torch.uint8, device=dplan.device)
+        self.launches = 0
+        self.algo_bytes = 0
+
+    # Q0 (single_gpu.py:30-32)
+    def load(self, image: torch.Tensor):
+        _require_cuda(image, "image")
+        p = self.plan
+        if tuple(image.shape) != (self.B, p.H, p.W, 3) or image.dtype != torch.float32:
+            raise ValueError(f"image must be float32 [{self.B},{p.H},{p.W},3], got {image.dtype} {tuple(image.shape)}")
+        image = image.contiguous()
+        nat.quantize_canvas(image.data_ptr(), self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, _stream_ptr())
+        self.launches += 1
+        return self
+
+    def clone(self) -> "Canvas":
+        c = Canvas(self.dp, self.B)
+        c.buf.copy_(self.buf)
+        return c
+
+    def result(self) -> torch.Tensor:
+        p = self.plan
+        out = torch.empty((self.B, p.H, p.W, 3), dtype=torch.float32, device=self.buf.device)
+        nat.dequantize_canvas(self.buf.data_ptr(), out.data_ptr(), self.B, p.H, p.W, self.pitch, _stream_ptr())
+        self.launches += 1
+        return out
+
+    def result_u8(self) -> torch.Tensor:
+        return self.buf[:, :, : self.plan.W * 3].reshape(self.B, self.plan.H, self.plan.W, 3)
+
+    # K2 (tile_ops.py:96-155)
+    def crop(self, tile_ids: Sequence[int], out: Optional[torch.Tensor] = None):
+        """-> (flat fp32 buffer, element offsets per tile).  Tile i is
+        buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
+        tile_ids = tuple(int(t) for t in tile_ids)
+        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B)
+        if out is None:
+            out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
+        elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError("crop: `out` too small or wrong dtype/device")
+        p = self.plan
+        nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
+                             self.dp.tabs.data_ptr(), items.data_ptr(), items.shape[0], wl.patch_w, wl.patch_h,
+                             out.data_ptr(), _stream_ptr())
+        self.launches += 1
+        self.algo_bytes += wl.algo_bytes * self.B
+        return out, offs
+
+    # K4 (tile_ops.py:310-349 after the truncating cast of single_gpu.py:60)
+    def blend(self, tile_ids: Sequence[int], src: torch.Tensor, offs: np.ndarray):
+        """Composite processed tiles into the canvas in the ORDER of `tile_ids`.
+        src: flat fp32 (sampler output) or uint8 (already quantised) buffer."""
+        _require_cuda(src, "src")
+        tile_ids = tuple(int(t) for t in tile_ids)
+        if src.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
+        src_u8 = src.dtype == torch.uint8
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8)
+        if items.shape[0] == 0:
+            return
+        p = self.plan
+        src = src.contiguous()
+        nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
+                       self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(), items.shape[0],
+                       cover.data_ptr(), wl.patch_w, wl.patch_h, src.data_ptr(), src_u8, _stream_ptr())
+        self.launches += 1
+        self.algo_bytes += wl.algo_bytes * self.B
+
+
+def tile_views(plan: Plan, tile_ids: Sequence[int], buf: torch.Tensor, offs: np.ndarray, B: int):
+    """Group consecutive same-shape tiles of a packed buffer into [n, B, ph, pw, 3] views."""
+    groups = []
+    i = 0
+    ids = list(tile_ids)
+    while i < len(ids):
+        t = plan.tiles[ids[i]]
+        j = i
+        while j + 1 < len(ids) and (plan.tiles[ids[j + 1]].pw, plan.tiles[ids[j + 1]].ph) == (t.pw, t.ph):
+            j += 1
+        n = j - i + 1
+        sz = B * t.ph * t.pw * 3
+        view = buf[int(offs[i]): int(offs[i]) + n * sz].view(n, B, t.ph, t.pw, 3)
+        groups.append((ids[i:j + 1], view))
+        i = j + 1
+    return groups
+
+
+def denoise_packed(plan: Plan, tile_ids: Sequence[int], buf: torch.Tensor, offs: np.ndarray, B: int,
+                   denoiser: Denoiser) -> torch.Tensor:
+    groups = tile_views(plan, tile_ids, buf, offs, B)
+    if len(groups) == 1:   # uniform tiles: the sampler's output IS the packed buffer
+        ids, view = groups[0]
+        res = denoiser(view, [plan.tiles[i] for i in ids])
+        if tuple(res.shape) != tuple(view.shape):
+            raise ValueError(f"denoiser returned {tuple(res.shape)}, expected {tuple(view.shape)}")
+        _require_cuda(res, "denoiser output")
+        return res.to(torch.float32).contiguous().view(-1)
+    out = torch.empty_like(buf)
+    for ids, view in groups:
+        res = denoiser(view, [plan.tiles[i] for i in ids])
+        if tuple(res.shape) != tuple(view.shape):
+            raise ValueError(f"denoiser returned {tuple(res.shape)}, expected {tuple(view.shape)}")
+        _require_cuda(res, "denoiser output")
+        o0 = int(offs[list(tile_ids).index(ids[0])])
+        out[o0: o0 + view.numel()].view_as(view).copy_(res.to(torch.float32))
+    return out
+
+
+def _sorted_by_shape(plan: Plan, ids: Sequence[int]) -> List[int]:
+    return sorted(ids, key=lambda i: (plan.tiles[i].ph, plan.tiles[i].pw, i))
+
+
+def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, keep_processed: bool = False):
+    """Process `order` (tile ids) with the reference's progressive semantics on `canvas`
+    (single_gpu.py:40-64 / static.py:242-280): wave by wave, each wave = crop kernel,
+    one sampler call, blend kernel.  Returns {tile id: u8 processed tile [B,ph,pw,3]}
+    when keep_processed (what a static-mode worker ships to the master)."""
+    plan, B = canvas.plan, canvas.B
+    shipped: Dict[int, torch.Tensor] = {}
+    for wave in plan.waves(order):
+        wave = _sorted_by_shape(plan, wave)
+        buf, offs = canvas.crop(wave)
+        out = denoise_packed(plan, wave, buf, offs, B, denoiser)
+        canvas.blend(wave, out, offs)
+        if keep_processed:
+            q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
+            nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
+            canvas.launches += 1
+            for i, tid in enumerate(wave):
+                t = plan.tiles[tid]
+                n = B * t.ph * t.pw * 3
+                shipped[tid] = q[int(offs[i]): int(offs[i]) + n].view(B, t.ph, t.pw, 3)
+    return shipped
+
+
+def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
+                   mask_blur: int, force_uniform_tiles: bool = True, stats: Optional[dict] = None) -> torch.Tensor:
+    """One-GPU job on a CUDA image [B,H,W,3] fp32 -> fp32 (values k/255), exact
+    progressive semantics of process_single_gpu."""
+    _require_cuda(image, "image")
+    B, H, W, _ = image.shape
+    plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
+    with torch.cuda.device(image.device):
+        dp = DevicePlan.get(plan, image.device)
+        canvas = Canvas(dp, B).load(image)
+        run_progressive(canvas, range(len(plan.tiles)), denoiser)
+        res = canvas.result()
+    if stats is not None:
+        stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches
+        stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes
+        stats["tiles"] = len(plan.tiles)
+        stats["waves"] = len(plan.waves())
+    return res

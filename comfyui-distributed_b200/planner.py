@@ -1,0 +1,404 @@
+"""Host-side planner of the USDU tile path: geometry, resample tables, feather-template
+classes, dependency waves, rank partitions and the kernel work lists.
+
+Everything here is integer bookkeeping that the reference recomputes per tile with
+full-canvas PIL images; here it is computed once per job (and cached per geometry):
+
+* tile grid ............ upscale/tile_ops.py:14-32 (round_to_multiple, calculate_tiles)
+* crop window .......... upscale/tile_ops.py:51-82 / :108-138 with
+                         utils/usdu_utils.py:49-112 (get_crop_region, fix_crop_region,
+                         expand_crop)
+* progressive order .... upscale/modes/single_gpu.py:40-64 (tile k sees tiles < k)
+* static partition ..... upscale/modes/static.py:226-311 (pull queue) -> a fixed plan
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+
+# --------------------------------------------------------------------------------------
+# geometry
+# --------------------------------------------------------------------------------------
+def round_to_multiple(value: int, multiple: int = 8) -> int:
+    # Python's round(): ties go to the even multiple, exactly as upscale/tile_ops.py:14-16
+    return round(value / multiple) * multiple
+
+
+def tile_origins(W: int, H: int, tw: int, th: int) -> List[Tuple[int, int]]:
+    cols, rows = math.ceil(W / tw), math.ceil(H / th)
+    return [(c * tw, r * th) for r in range(rows) for c in range(cols)]
+
+
+def _grow(lo: int, hi: int, limit: int, target: int) -> Tuple[int, int]:
+    """One axis of expand_crop (utils/usdu_utils.py:88-110): right/bottom by half the
+    deficit, then left/top by what is still missing, then right/bottom again."""
+    hi = min(hi + (target - (hi - lo)) // 2, limit)
+    lo = max(lo - (target - (hi - lo)), 0)
+    hi = min(hi + (target - (hi - lo)), limit)
+    return lo, hi
+
+
+@dataclass(frozen=True)
+class Tile:
+    idx: int
+    x: int          # grid origin
+    y: int
+    x1: int         # crop window on the canvas
+    y1: int
+    x2: int
+    y2: int
+    pw: int         # processing size
+    ph: int
+    bx1: int        # bbox of the inclusive mask rectangle, clipped (exclusive right/bottom)
+    by1: int
+    bx2: int
+    by2: int
+
+    @property
+    def ew(self) -> int:
+        return self.x2 - self.x1
+
+    @property
+    def eh(self) -> int:
+        return self.y2 - self.y1
+
+    @property
+    def region(self) -> Tuple[int, int, int, int]:
+        return (self.x1, self.y1, self.x2, self.y2)
+
+
+def make_tile(idx: int, W: int, H: int, x: int, y: int, tw: int, th: int, padding: int, uniform: bool) -> Tile:
+    # PIL draws the rectangle [x, y, x+tw, y+th] INCLUSIVE of its far corner; getbbox is
+    # exclusive, hence the +1 (upscale/tile_ops.py:51-54, utils/usdu_utils.py:52).
+    bx1, by1 = x, y
+    bx2, by2 = min(x + tw + 1, W), min(y + th + 1, H)
+    x1, y1 = max(bx1 - padding, 0), max(by1 - padding, 0)
+    x2, y2 = min(bx2 + padding, W), min(by2 + padding, H)
+    if x2 < W:
+        x2 -= 1
+    if y2 < H:
+        y2 -= 1
+    if uniform:
+        pw, ph = round_to_multiple(tw + padding), round_to_multiple(th + padding)
+        cw, ch = x2 - x1, y2 - y1
+        crop_ratio = cw / ch if ch else 1.0
+        proc_ratio = pw / ph if ph else 1.0
+        if crop_ratio > proc_ratio:
+            want_w, want_h = cw, (round(cw / proc_ratio) if proc_ratio else ch)
+        else:
+            want_w, want_h = round(ch * proc_ratio), ch
+    else:
+        pw = want_w = max(8, math.ceil((x2 - x1) / 8) * 8)
+        ph = want_h = max(8, math.ceil((y2 - y1) / 8) * 8)
+    x1, x2 = _grow(x1, x2, W, want_w)
+    y1, y2 = _grow(y1, y2, H, want_h)
+    return Tile(idx, x, y, x1, y1, x2, y2, pw, ph, bx1, by1, bx2, by2)
+
+
+def _overlap(a: Tuple[int, int, int, int], b: Tuple[int, int, int, int]) -> bool:
+    return a[0] < b[2] and b[0] < a[2] and a[1] < b[3] and b[1] < a[3]
+
+
+# --------------------------------------------------------------------------------------
+# plan
+# --------------------------------------------------------------------------------------
+@dataclass
+class WorkList:
+    """Device work list for one kernel launch (numpy, uploaded by the engine)."""
+    items: np.ndarray                 # int32 [n, words]
+    cover: Optional[np.ndarray]       # int32 [m, COVER_WORDS] (blend only)
+    patch_w: int
+    patch_h: int
+    algo_bytes: int                   # algorithmic HBM bytes of the launch per frame
+
+
+@dataclass
+class Plan:
+    W: int
+    H: int
+    tile_width: int
+    tile_height: int
+    padding: int
+    mask_blur: int
+    uniform: bool
+    tw: int = 0
+    th: int = 0
+    tiles: List[Tile] = field(default_factory=list)
+    tile_desc: np.ndarray = None          # int32 [T, TILE_WORDS]
+    tabs: np.ndarray = None               # int32 pool
+    mask_specs: np.ndarray = None         # int32 [n_cls, MASK_WORDS]
+    mask_pool_bytes: int = 0
+    mask_class: List[int] = field(default_factory=list)
+    neighbors: List[List[int]] = field(default_factory=list)   # overlapping windows, any order
+    _tab_off: Dict[Tuple[int, int], int] = field(default_factory=dict)
+    _tab_span: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
+
+    # ---- construction ---------------------------------------------------------------
+    @staticmethod
+    def build(W: int, H: int, tile_width: int, tile_height: int, padding: int, mask_blur: int,
+              uniform: bool) -> "Plan":
+        p = Plan(W, H, tile_width, tile_height, padding, mask_blur, uniform)
+        p.tw, p.th = round_to_multiple(tile_width), round_to_multiple(tile_height)
+        if p.tw <= 0 or p.th <= 0:
+            raise ValueError(f"tile size rounds to zero: {tile_width}x{tile_height}")
+        p.tiles = [make_tile(i, W, H, x, y, p.tw, p.th, padding, uniform)
+                   for i, (x, y) in enumerate(tile_origins(W, H, p.tw, p.th))]
+        p._build_tables()
+        p._build_masks()
+        p._build_descriptors()
+        p._build_neighbors()
+        return p
+
+    def _table(self, n_in: int, n_out: int) -> int:
+        if n_in == n_out:
+            return -1
+        key = (n_in, n_out)
+        if key not in self._tab_off:
+            tab = nat.build_resample_table(n_in, n_out)
+            off = 0 if self.tabs is None else int(self.tabs.shape[0])
+            self.tabs = tab if self.tabs is None else np.concatenate([self.tabs, tab])
+            self._tab_off[key] = off
+            b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
+            self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + b[:, 1]], 1)   # [lo, hi) per output
+        return self._tab_off[key]
+
+    def _build_tables(self):
+        for t in self.tiles:
+            self._table(t.ew, t.pw), self._table(t.eh, t.ph)
+            self._table(t.pw, t.ew), self._table(t.ph, t.eh)
+        if self.tabs is None:
+            self.tabs = np.zeros(nat.TAB_HEADER, dtype=np.int32)
+
+    def _ramp(self) -> int:
+        """Pixels beyond the rectangle that the blurred mask can be non-zero (3 box
+        passes of half-width rad+1 each)."""
+        if self.mask_blur <= 0:
+            return 0
+        rad, _, _ = nat.box_blur_params(self.mask_blur)
+        return 3 * (rad + 1)
+
+    def _build_masks(self):
+        ext = self._ramp()
+        classes: Dict[tuple, int] = {}
+        specs = []
+        off = 0
+        self.mask_class = []
+        self._mask_off, self._mask_pitch = [], []
+        for t in self.tiles:
+            kh = (t.bx1 - t.x1, t.bx2 - t.x1, t.ew, min(t.x1, ext), min(self.W - t.x2, ext))
+            kv = (t.by1 - t.y1, t.by2 - t.y1, t.eh, min(t.y1, ext), min(self.H - t.y2, ext))
+            key = (kh, kv)
+            if key not in classes:
+                classes[key] = len(specs)
+                pitch = (t.ew + 15) // 16 * 16
+                specs.append([self.W, self.H, t.bx1, t.by1, t.bx2, t.by2, t.x1, t.y1, t.x2, t.y2,
+                              self.mask_blur, off, pitch, 0, 0, 0])
+                off += pitch * t.eh
+                off = (off + 255) // 256 * 256
+            c = classes[key]
+            self.mask_class.append(c)
+            self._mask_off.append(specs[c][11])
+            self._mask_pitch.append(specs[c][12])
+        self.mask_specs = np.asarray(specs, dtype=np.int32)
+        self.mask_pool_bytes = max(off, 256)
+        if self.mask_pool_bytes >= 2 ** 31:
+            raise ValueError("feather templates exceed 2 GiB")
+
+    def support(self, t: Tile) -> Tuple[int, int, int, int]:
+        """Window-relative bbox outside which the feather alpha is exactly 0."""
+        ext = self._ramp()
+        return (max(t.bx1 - ext, t.x1) - t.x1, max(t.by1 - ext, t.y1) - t.y1,
+                min(t.bx2 + ext, t.x2) - t.x1, min(t.by2 + ext, t.y2) - t.y1)
+
+    def _build_descriptors(self):
+        d = np.zeros((len(self.tiles), nat.TILE_WORDS), dtype=np.int32)
+        for t in self.tiles:
+            r = d[t.idx]
+            r[nat.T_X1], r[nat.T_Y1], r[nat.T_EW], r[nat.T_EH] = t.x1, t.y1, t.ew, t.eh
+            r[nat.T_PW], r[nat.T_PH] = t.pw, t.ph
+            r[nat.T_MASK_OFF], r[nat.T_MASK_PITCH] = self._mask_off[t.idx], self._mask_pitch[t.idx]
+            r[nat.T_TAB_CROP_H], r[nat.T_TAB_CROP_V] = self._table(t.ew, t.pw), self._table(t.eh, t.ph)
+            r[nat.T_TAB_BLEND_H], r[nat.T_TAB_BLEND_V] = self._table(t.pw, t.ew), self._table(t.ph, t.eh)
+            r[nat.T_SUP_X0:nat.T_SUP_Y1 + 1] = self.support(t)
+        self.tile_desc = d
+
+    def _build_neighbors(self):
+        """Tiles whose crop windows intersect (grid-bucketed, O(T * neighbours))."""
+        T = len(self.tiles)
+        self.neighbors = [[] for _ in range(T)]
+        if T <= 1:
+            return
+        cell = max(max(t.ew for t in self.tiles), max(t.eh for t in self.tiles))
+        buckets: Dict[Tuple[int, int], List[int]] = {}
+        for t in self.tiles:
+            for gx in range(t.x1 // cell, (t.x2 - 1) // cell + 1):
+                for gy in range(t.y1 // cell, (t.y2 - 1) // cell + 1):
+                    buckets.setdefault((gx, gy), []).append(t.idx)
+        seen = set()
+        for ids in buckets.values():
+            for a in range(len(ids)):
+                for b in range(a + 1, len(ids)):
+                    i, j = ids[a], ids[b]
+                    if (i, j) in seen:
+                        continue
+                    seen.add((i, j))
+                    if _overlap(self.tiles[i].region, self.tiles[j].region):
+                        self.neighbors[i].append(j)
+                        self.neighbors[j].append(i)
+
+    # ---- schedules -------------------------------------------------------------------
+    def waves(self, order: Optional[Sequence[int]] = None) -> List[List[int]]:
+        """Level schedule of an ordered tile list under progressive semantics: tile k must
+        see the blends of every earlier tile whose window intersects its own.  Tiles of
+        one wave have pairwise disjoint windows, so they can be cropped, denoised and
+        blended together; running the waves in sequence reproduces the sequential loop
+        of upscale/modes/single_gpu.py:40-64 exactly."""
+        order = list(range(len(self.tiles))) if order is None else list(order)
+        pos = {t: i for i, t in enumerate(order)}
+        level: Dict[int, int] = {}
+        out: List[List[int]] = []
+        for t in order:
+            lv = 0
+            for n in self.neighbors[t]:
+                if n in pos and pos[n] < pos[t]:
+                    lv = max(lv, level[n] + 1)
+            level[t] = lv
+            while len(out) <= lv:
+                out.append([])
+            out[lv].append(t)
+        return out
+
+    def conflict_free(self, assignment: Sequence[Sequence[int]]) -> bool:
+        for tiles in assignment:
+            s = set(tiles)
+            for t in tiles:
+                if any(n in s for n in self.neighbors[t]):
+                    return False
+        return True
+
+    def partition(self, world: int) -> List[List[int]]:
+        """Static tile -> rank plan replacing the reference's pull queue
+        (upscale/modes/static.py:226-311).  Tries skewed colourings rank = (col + k*row)
+        mod world that leave no rank with two window-overlapping tiles (then every crop
+        comes from the original canvas and all ranks run fully in parallel); falls back
+        to round-robin, which the engine executes as per-rank waves."""
+        T = len(self.tiles)
+        if world <= 1:
+            return [list(range(T))]
+        cols = math.ceil(self.W / self.tw)
+        best = None
+        for k in range(1, world):
+            asg = [[] for _ in range(world)]
+            for t in self.tiles:
+                asg[((t.idx % cols) + k * (t.idx // cols)) % world].append(t.idx)
+            if self.conflict_free(asg):
+                spread = max(len(a) for a in asg) - min(len(a) for a in asg)
+                if best is None or spread < best[0]:
+                    best = (spread, asg)
+        if best is not None:
+            return best[1]
+        asg = [[] for _ in range(world)]
+        for t in self.tiles:
+            asg[t.idx % world].append(t.idx)
+        return asg
+
+    # ---- kernel work lists -----------------------------------------------------------
+    def slot_offsets(self, tile_ids: Sequence[int], B: int) -> Tuple[np.ndarray, int]:
+        """Element offsets of each tile's [B, ph, pw, 3] block in a packed buffer."""
+        offs = np.zeros(len(tile_ids), dtype=np.int64)
+        cur = 0
+        for i, tid in enumerate(tile_ids):
+            t = self.tiles[tid]
+            offs[i] = cur
+            cur += B * t.ph * t.pw * 3
+        return offs, cur
+
+    def _span_max(self, n_in: int, n_out: int, block: int, aligned: bool) -> int:
+        """Largest input extent read by `block` consecutive outputs of an axis."""
+        if n_in == n_out:
+            return min(block, n_out)
+        sp = self._tab_span[(n_in, n_out)]
+        starts = np.arange(0, n_out, block) if aligned else np.arange(0, n_out)
+        ends = np.minimum(starts + block, n_out) - 1
+        return int((sp[ends, 1] - sp[starts, 0]).max())
+
+    def crop_worklist(self, tile_ids: Sequence[int], B: int) -> Tuple[WorkList, np.ndarray, int]:
+        offs, total = self.slot_offsets(tile_ids, B)
+        rows = []
+        pw_max = ph_max = 1
+        nbytes = 0
+        for i, tid in enumerate(tile_ids):
+            t = self.tiles[tid]
+            ox = np.arange(0, t.pw, nat.BLOCK_W, dtype=np.int64)
+            oy = np.arange(0, t.ph, nat.BLOCK_H, dtype=np.int64)
+            gx, gy = np.meshgrid(ox, oy)
+            n = gx.size
+            it = np.zeros((n, nat.CROP_ITEM_WORDS), dtype=np.int64)
+            it[:, 0], it[:, 1], it[:, 2] = tid, gx.ravel(), gy.ravel()
+            it[:, 3], it[:, 4] = offs[i] & 0xFFFFFFFF, offs[i] >> 32
+            rows.append(it)
+            pw_max = max(pw_max, self._span_max(t.ew, t.pw, nat.BLOCK_W, True))
+            ph_max = max(ph_max, self._span_max(t.eh, t.ph, nat.BLOCK_H, True))
+            nbytes += t.ew * t.eh * 3 + t.pw * t.ph * 3 * 4      # u8 window read + fp32 tile write
+        items = np.concatenate(rows, 0) if rows else np.zeros((0, nat.CROP_ITEM_WORDS), dtype=np.int64)
+        items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
+        return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes), offs, total
+
+    def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4) -> WorkList:
+        """Canvas blocks touched by the given tiles; each block lists its tiles in the
+        given order (the order of `tile_ids` IS the blend order)."""
+        bw, bh = nat.BLOCK_W, nat.BLOCK_H
+        nbx = (self.W + bw - 1) // bw
+        keys, tids, seq = [], [], []
+        pw_max = ph_max = 1
+        nbytes = 0
+        for s, tid in enumerate(tile_ids):
+            t = self.tiles[tid]
+            sx0, sy0, sx1, sy1 = self.support(t)
+            if sx1 <= sx0 or sy1 <= sy0:
+                continue
+            X0, Y0, X1, Y1 = t.x1 + sx0, t.y1 + sy0, t.x1 + sx1, t.y1 + sy1
+            gx = np.arange(X0 // bw, (X1 - 1) // bw + 1, dtype=np.int64)
+            gy = np.arange(Y0 // bh, (Y1 - 1) // bh + 1, dtype=np.int64)
+            k = (gy[:, None] * nbx + gx[None, :]).ravel()
+            keys.append(k)
+            tids.append(np.full(k.size, tid, dtype=np.int64))
+            seq.append(np.full(k.size, s, dtype=np.int64))
+            pw_max = max(pw_max, self._span_max(t.pw, t.ew, bw, False))
+            ph_max = max(ph_max, self._span_max(t.ph, t.eh, bh, False))
+            nbytes += t.pw * t.ph * 3 * src_bytes_per_elem + 2 * (sx1 - sx0) * (sy1 - sy0) * 3
+        if not keys:
+            return WorkList(np.zeros((0, nat.BLEND_ITEM_WORDS), np.int32), np.zeros((0, nat.COVER_WORDS), np.int32), 1, 1, 0)
+        keys, tids, seq = np.concatenate(keys), np.concatenate(tids), np.concatenate(seq)
+        order = np.lexsort((seq, keys))             # by block, then by position in tile_ids
+        keys, tids, seq = keys[order], tids[order], seq[order]
+        first = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
+        counts = np.diff(np.r_[first, keys.size])
+        items = np.zeros((first.size, nat.BLEND_ITEM_WORDS), dtype=np.int64)
+        items[:, 0] = (keys[first] % nbx) * bw
+        items[:, 1] = (keys[first] // nbx) * bh
+        items[:, 2] = first
+        items[:, 3] = counts
+        cover = np.zeros((keys.size, nat.COVER_WORDS), dtype=np.int64)
+        o = np.asarray(offs, dtype=np.int64)[seq]
+        cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32
+        return WorkList(np.ascontiguousarray(items.astype(np.uint32).view(np.int32)),
+                        np.ascontiguousarray(cover.astype(np.uint32).view(np.int32)), pw_max, ph_max, nbytes)
+
+
+_PLAN_CACHE: Dict[tuple, Plan] = {}
+
+
+def get_plan(W: int, H: int, tile_width: int, tile_height: int, padding: int, mask_blur: int, uniform: bool) -> Plan:
+    key = (W, H, tile_width, tile_height, padding, mask_blur, bool(uniform))
+    if key not in _PLAN_CACHE:
+        if len(_PLAN_CACHE) > 16:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = Plan.build(*key)
+    return _PLAN_CACHE[key]

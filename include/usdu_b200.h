@@ -1,0 +1,162 @@
+/*
+ * usdu_b200.h -- C ABI of libusdu_b200.so: the B200-native (sm_100a) replacement for the
+ * CPU/Pillow pixel path of ComfyUI-Distributed's Ultimate-SD-Upscale tile pipeline.
+ *
+ * The boundary is plain C: raw pointers, sizes, a CUDA stream handle passed as void*.
+ * No torch types.  Device pointers are marked _dev; everything else is host memory.
+ * Every entry point returns 0 on success or a negative usdu_status; the message of the
+ * last failure on the calling thread is available from usdu_last_error().  There is no
+ * CPU fallback: without a CUDA device every compute entry point fails with
+ * USDU_ERR_CUDA.
+ *
+ * Reference interfaces replaced (file:line are relative to robertvoy/ComfyUI-Distributed
+ * @ a91f9fb):
+ *   utils/image.py:8-18                tensor_to_pil / pil_to_tensor
+ *   upscale/tile_ops.py:34-155         extract_[batch_]tile_with_padding (crop + LANCZOS)
+ *   upscale/tile_ops.py:289-308        create_tile_mask (rectangle + GaussianBlur)
+ *   upscale/tile_ops.py:310-349        blend_tile (LANCZOS back + alpha composite)
+ *   upscale/worker_comms.py:16-108     tile payload packing (PNG) -> usdu_pack_tiles_u8
+ * The geometry (upscale/tile_ops.py:14-32, utils/usdu_utils.py:49-112) stays on the host
+ * in Python, like the reference; it produces the descriptor arrays documented below.
+ */
+#ifndef USDU_B200_H
+#define USDU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define USDU_ABI_VERSION 1
+
+typedef enum usdu_status {
+    USDU_OK = 0,
+    USDU_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, misaligned pitch ...) */
+    USDU_ERR_CUDA = -2,      /* CUDA runtime error (no device, launch failure ...) */
+    USDU_ERR_UNSUPPORTED = -3
+} usdu_status;
+
+/* ---- descriptor layouts (all int32, little endian, device-resident unless noted) ------
+ *
+ * Tile descriptor: USDU_TILE_WORDS int32 per tile position (geometry is identical for all
+ * frames of a batch, upscale/tile_ops.py:108-138).
+ */
+#define USDU_TILE_WORDS 16
+#define USDU_T_X1 0          /* crop window origin on the canvas */
+#define USDU_T_Y1 1
+#define USDU_T_EW 2          /* crop window ("extracted") size */
+#define USDU_T_EH 3
+#define USDU_T_PW 4          /* processing size handed to the sampler */
+#define USDU_T_PH 5
+#define USDU_T_MASK_OFF 6    /* byte offset of this tile's feather template in the mask pool */
+#define USDU_T_MASK_PITCH 7  /* bytes per template row (>= EW) */
+#define USDU_T_TAB_CROP_H 8  /* int32 offset of a resample table in the table pool, -1 = identity */
+#define USDU_T_TAB_CROP_V 9  /*   crop:  EW->PW (H), EH->PH (V) */
+#define USDU_T_TAB_BLEND_H 10 /*  blend: PW->EW (H), PH->EH (V) */
+#define USDU_T_TAB_BLEND_V 11
+#define USDU_T_SUP_X0 12     /* bbox of the template's non-zero alpha, window coordinates */
+#define USDU_T_SUP_Y0 13
+#define USDU_T_SUP_X1 14
+#define USDU_T_SUP_Y1 15
+
+/* Resample table at int32 offset o of the table pool:
+ *   [o+0]=in_size [o+1]=out_size [o+2]=ksize [o+3]=0
+ *   [o+4 ...]            bounds: out_size x {first input index, tap count}
+ *   [o+4+2*out_size ...] kk: out_size x ksize coefficients, 22-bit fixed point
+ * (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc.) */
+#define USDU_TAB_HEADER 4
+
+/* Crop work item: one BHxBW block of one tile's processing-size output. */
+#define USDU_CROP_ITEM_WORDS 6
+/*   [0]=tile id [1]=ox0 [2]=oy0 [3]=out offset lo [4]=out offset hi [5]=0
+ *   out offset: element offset of this tile's [B][PH][PW][3] block in `out`. */
+
+/* Blend work item: one canvas block and the ordered list of tiles composited into it. */
+#define USDU_BLEND_ITEM_WORDS 4
+/*   [0]=block x0 [1]=block y0 [2]=first cover entry [3]=cover count */
+#define USDU_COVER_WORDS 4
+/*   [0]=tile id [1]=src offset lo [2]=src offset hi [3]=0
+ *   src offset: element offset of the tile's [B][PH][PW][3] processed block in `src`.
+ *   Entries of one item are applied in list order (ascending tile id reproduces
+ *   upscale/modes/static.py:521-553). */
+
+/* Feather-mask spec (host array, USDU_MASK_WORDS int32 each). */
+#define USDU_MASK_WORDS 16
+/*   [0]=W [1]=H canvas; [2..5]=bx1,by1,bx2,by2 clipped inclusive-rectangle bbox (exclusive
+ *   right/bottom); [6..9]=x1,y1,x2,y2 window; [10]=blur radius (mask_blur, 0 = none);
+ *   [11]=out byte offset in the mask pool; [12]=out pitch; [13..15]=0 */
+
+/* canvas block edge used by the blend / crop kernels (pixels) */
+#define USDU_BLOCK_W 64
+#define USDU_BLOCK_H 32
+
+/* ---- library ------------------------------------------------------------------------ */
+int usdu_abi_version(void);
+const char* usdu_last_error(void);
+/* number of CUDA devices visible, or a negative usdu_status */
+int usdu_device_count(void);
+
+/* ---- host-side table builders (exact Pillow arithmetic, C double / C float) -------- */
+/* taps per output for an in->out LANCZOS axis (Resample.c: ceil(3*max(in/out,1))*2+1) */
+int usdu_resample_ksize(int in_size, int out_size);
+/* number of int32 words of a table: USDU_TAB_HEADER + out*(2+ksize) */
+int64_t usdu_resample_table_words(int in_size, int out_size);
+/* fill `table` (host, usdu_resample_table_words() int32) */
+int usdu_build_resample_table(int in_size, int out_size, int32_t* table);
+/* ImageFilter.GaussianBlur(radius) -> extended-box parameters (BoxBlur.c, 3 passes) */
+int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw);
+
+/* ---- device kernels ----------------------------------------------------------------- */
+/* Q0: canvas_u8[b][y][x*3+c] = (uint8)(255.f * img[b][y][x][c])   (utils/image.py:8-10)
+ * pitch = bytes per canvas row (>= 3*W, multiple of 16); frame stride = H*pitch. */
+int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W,
+                         int64_t pitch, void* stream);
+/* canvas u8 -> fp32 image (u / 255.0f, utils/image.py:12-14) */
+int usdu_dequantize_canvas(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W,
+                           int64_t pitch, void* stream);
+/* Q1 for transport: dst[i] = (uint8)(255.f * src[i]); n elements (worker_comms.py:30-33) */
+int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* stream);
+/* receiving side of the transport: dst[i] = src[i] / 255.0f (api/job_routes.py:104-132) */
+int usdu_unpack_tiles_f32(const uint8_t* src_dev, float* dst_dev, int64_t n, void* stream);
+
+/* Feather templates: n_specs masks into mask_pool_dev.  scratch_dev needs
+ * usdu_mask_scratch_bytes(specs, n) bytes. */
+int64_t usdu_mask_scratch_bytes(const int32_t* specs_host, int n_specs);
+int usdu_build_feather_masks(const int32_t* specs_host, int n_specs, uint8_t* mask_pool_dev,
+                             uint8_t* scratch_dev, void* stream);
+
+/* Tile crop + LANCZOS resize: canvas u8 -> fp32 tiles (values k/255).
+ * grid = n_items x B blocks.  out_dev holds [B][PH][PW][3] fp32 per tile at the item's
+ * out offset.  patch_w x patch_h (pixels) is the largest input patch any item reads (the
+ * planner knows it from the resample tables); it sizes the shared-memory staging. */
+int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
+                          const int32_t* tiles_dev, const int32_t* tabs_dev,
+                          const int32_t* items_dev, int n_items, int patch_w, int patch_h,
+                          float* out_dev, void* stream);
+
+/* Seam blend: for every item (canvas block) apply its cover list in order:
+ * quantise (fp32 source) -> LANCZOS back to the crop size -> integer alpha composite
+ * with the tile's feather template, in place on the canvas.
+ * src_is_u8 = 0: src_dev is fp32 sampler output in [0,1]; 1: src_dev is u8 (already Q1).
+ * patch_w x patch_h: largest processed-tile patch any (item, cover entry) reads.
+ * Tiles whose crop windows overlap must not be blended by different items of one launch
+ * unless they appear in the same item's cover list (items own disjoint canvas blocks, so
+ * any cover list is race-free; ORDER across overlapping tiles is the cover-list order). */
+int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
+                    const int32_t* tiles_dev, const int32_t* tabs_dev,
+                    const uint8_t* mask_pool_dev, const int32_t* items_dev, int n_items,
+                    const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
+                    int src_is_u8, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* USDU_B200_H */

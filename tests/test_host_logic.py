@@ -1,0 +1,140 @@
+"""CPU tests of the host side: planner geometry against the reference fixtures, the
+C-ABI library (loads, exports every declared symbol, host-side table builders equal the
+oracle), schedules and work lists.  No compute calls on a device."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import usdu_oracle as orc
+from __graft_entry__ import ROOT, load_package
+
+load_package()
+from comfyui_distributed_b200 import _native as nat  # noqa: E402
+from comfyui_distributed_b200 import planner  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+GEO = json.load(open(os.path.join(G, "geometry.json")))["cases"]
+HEADER = open(os.path.join(ROOT, "include", "usdu_b200.h")).read()
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(usdu_\w+)\s*\(", HEADER, re.M))
+    assert declared, "no declarations parsed from include/usdu_b200.h"
+    assert declared == set(nat.EXPORTS)
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.usdu_abi_version() == int(re.search(r"#define USDU_ABI_VERSION (\d+)", HEADER).group(1))
+
+
+def test_binding_constants_match_header():
+    for cname, val in [("USDU_TILE_WORDS", nat.TILE_WORDS), ("USDU_TAB_HEADER", nat.TAB_HEADER),
+                       ("USDU_CROP_ITEM_WORDS", nat.CROP_ITEM_WORDS), ("USDU_BLEND_ITEM_WORDS", nat.BLEND_ITEM_WORDS),
+                       ("USDU_COVER_WORDS", nat.COVER_WORDS), ("USDU_MASK_WORDS", nat.MASK_WORDS),
+                       ("USDU_BLOCK_W", nat.BLOCK_W), ("USDU_BLOCK_H", nat.BLOCK_H),
+                       ("USDU_T_TAB_BLEND_V", nat.T_TAB_BLEND_V), ("USDU_T_SUP_Y1", nat.T_SUP_Y1),
+                       ("USDU_T_MASK_PITCH", nat.T_MASK_PITCH)]:
+        assert int(re.search(rf"#define {cname} (\d+)", HEADER).group(1)) == val, cname
+
+
+def test_error_reporting_without_device_or_with_bad_args():
+    lib = nat.lib()
+    assert lib.usdu_resample_ksize(0, 5) < 0
+    assert b"positive" in lib.usdu_last_error()
+    with pytest.raises(nat.NativeError):
+        nat.quantize_canvas(0, 0, 1, 1, 1, 16, 0)      # null pointers are rejected before any CUDA call
+    with pytest.raises(nat.NativeError):
+        nat.tile_blend(1, 1, 8, 8, 17, 1, 1, 1, 1, 1, 1, 8, 8, 0, 0, 0)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(576, 544), (544, 576), (320, 288), (288, 544), (100, 160), (1, 8), (2304, 1152), (37, 64)])
+def test_resample_table_equals_oracle(n_in, n_out):
+    tab = nat.build_resample_table(n_in, n_out)
+    bounds, kk = orc.lanczos_coeffs(n_in, n_out)
+    assert tab[0] == n_in and tab[1] == n_out and tab[2] == kk.shape[1]
+    assert np.array_equal(tab[4:4 + 2 * n_out].reshape(n_out, 2), bounds)
+    assert np.array_equal(tab[4 + 2 * n_out:].reshape(n_out, -1), kk)
+
+
+def test_box_blur_params_equal_oracle_for_every_radius():
+    for r in range(1, 257):
+        assert nat.box_blur_params(r) == orc.box_blur_params(r), r
+
+
+@pytest.mark.parametrize("case", GEO, ids=lambda c: f"{c['W']}x{c['H']}_t{c['tile_w']}x{c['tile_h']}_p{c['padding']}_{'u' if c['uniform'] else 'n'}")
+def test_planner_geometry_matches_reference(case):
+    p = planner.Plan.build(case["W"], case["H"], case["tile_w"], case["tile_h"], case["padding"], 8, case["uniform"])
+    assert (p.tw, p.th) == (case["tw"], case["th"])
+    rows = [[t.x, t.y, t.x1, t.y1, t.ew, t.eh, t.pw, t.ph] for t in p.tiles]
+    assert rows == case["rows"]
+
+
+def _windows_overlap(a, b):
+    return a.x1 < b.x2 and b.x1 < a.x2 and a.y1 < b.y2 and b.y1 < a.y2
+
+
+@pytest.mark.parametrize("W,H,tile,pad", [(7680, 4320, 512, 32), (1600, 1200, 512, 32), (1000, 900, 256, 64), (777, 333, 64, 128)])
+def test_neighbors_and_waves(W, H, tile, pad):
+    p = planner.Plan.build(W, H, tile, tile, pad, 8, True)
+    T = len(p.tiles)
+    for i in range(T):                                    # neighbour lists == brute force
+        brute = sorted(j for j in range(T) if j != i and _windows_overlap(p.tiles[i], p.tiles[j]))
+        assert sorted(p.neighbors[i]) == brute
+    waves = p.waves()
+    assert sorted(t for w in waves for t in w) == list(range(T))
+    level = {t: k for k, w in enumerate(waves) for t in w}
+    for w in waves:                                       # tiles of a wave are independent
+        for a in w:
+            assert not any(b in p.neighbors[a] for b in w)
+    for i in range(T):                                    # every dependency points to an earlier wave
+        for j in p.neighbors[i]:
+            if j < i:
+                assert level[j] < level[i]
+    if (W, H, tile) == (7680, 4320, 512):
+        assert len(waves) == 31 and max(len(w) for w in waves) == 8
+
+
+def test_partitions():
+    p = planner.get_plan(7680, 4320, 512, 512, 32, 8, True)
+    for world in (1, 2, 4, 8):
+        asg = p.partition(world)
+        assert sorted(t for a in asg for t in a) == list(range(135))
+        assert len(asg) == world
+        if world >= 4:
+            assert p.conflict_free(asg)
+            assert max(map(len, asg)) - min(map(len, asg)) <= 5
+    assert not p.conflict_free(p.partition(2))            # two ranks always own neighbours
+
+
+def test_mask_classes_and_worklists():
+    p = planner.get_plan(7680, 4320, 512, 512, 32, 8, True)
+    assert p.mask_specs.shape == (9, nat.MASK_WORDS)       # 3 x-classes x 3 y-classes
+    # equal class => equal template (checked with the oracle on one representative pair)
+    by_class = {}
+    for t in p.tiles:
+        by_class.setdefault(p.mask_class[t.idx], []).append(t)
+    for c, ts in by_class.items():
+        a, b = ts[0], ts[-1]
+        ma = orc.tile_mask_window(p.W, p.H, a.x, a.y, p.tw, p.th, 8, a.region)
+        mb = orc.tile_mask_window(p.W, p.H, b.x, b.y, p.tw, p.th, 8, b.region)
+        assert np.array_equal(ma, mb)
+        sx0, sy0, sx1, sy1 = p.support(a)                 # alpha is exactly 0 outside the support box
+        z = ma.copy()
+        z[sy0:sy1, sx0:sx1] = 0
+        assert not z.any()
+    ids = list(range(135))
+    wl, offs, total = p.crop_worklist(ids, 1)
+    assert total == 135 * 544 * 544 * 3
+    assert wl.items.shape == (135 * 9 * 17, nat.CROP_ITEM_WORDS)
+    bl = p.blend_worklist(ids, offs)
+    cov = bl.cover.reshape(-1, nat.COVER_WORDS)
+    for it in bl.items[::997]:                            # cover lists are ascending in tile id
+        c = cov[it[2]: it[2] + it[3], 0]
+        assert list(c) == sorted(c)
+    # every (tile, block) pair with intersecting support is present exactly once
+    assert bl.cover.shape[0] == sum(
+        ((t.x1 + p.support(t)[2] - 1) // 64 - (t.x1 + p.support(t)[0]) // 64 + 1) *
+        ((t.y1 + p.support(t)[3] - 1) // 32 - (t.y1 + p.support(t)[1]) // 32 + 1) for t in p.tiles)
