@@ -16,12 +16,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 1
-TILE_WORDS = 16
+ABI_VERSION = 2
+TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
 T_SUP_X0, T_SUP_Y0, T_SUP_X1, T_SUP_Y1 = 12, 13, 14, 15
-TAB_HEADER = 4
+T_FULL_X0, T_FULL_Y0, T_FULL_X1, T_FULL_Y1 = 16, 17, 18, 19
+TAB_HEADER = 8
+PACKED_ROW = 8
+FLAG_FAST = 1
 CROP_ITEM_WORDS = 6
 BLEND_ITEM_WORDS = 4
 COVER_WORDS = 4
@@ -43,6 +46,7 @@ _SIGNATURES = {
     "usdu_resample_ksize": (c_int, [c_int, c_int]),
     "usdu_resample_table_words": (c_int64, [c_int, c_int]),
     "usdu_build_resample_table": (c_int, [c_int, c_int, POINTER(c_int32)]),
+    "usdu_build_identity_table": (c_int, [c_int, POINTER(c_int32)]),
     "usdu_box_blur_params": (c_int, [c_float, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
@@ -51,9 +55,9 @@ _SIGNATURES = {
     "usdu_mask_scratch_bytes": (c_int64, [POINTER(c_int32), c_int]),
     "usdu_build_feather_masks": (c_int, [POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
     "usdu_tile_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
-                                      c_int, c_int, c_int, c_void_p, c_void_p]),
+                                      c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "usdu_tile_blend": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+                                c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -108,6 +112,12 @@ def build_resample_table(in_size: int, out_size: int) -> np.ndarray:
     return tab
 
 
+def build_identity_table(size: int) -> np.ndarray:
+    tab = np.zeros(TAB_HEADER + size * (3 + PACKED_ROW), dtype=np.int32)
+    _check(lib().usdu_build_identity_table(size, _i32p(tab)), "usdu_build_identity_table")
+    return tab
+
+
 def box_blur_params(radius: float):
     rad, ww, fw = c_int32(), c_uint32(), c_uint32()
     _check(lib().usdu_box_blur_params(float(radius), ctypes.byref(rad), ctypes.byref(ww), ctypes.byref(fw)),
@@ -145,12 +155,12 @@ def build_feather_masks(specs: np.ndarray, pool_ptr, scratch_ptr, stream):
 
 
 def tile_crop_resize(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, items_ptr, n_items, patch_w, patch_h,
-                     out_ptr, stream):
+                     out_ptr, flags, stream):
     _check(lib().usdu_tile_crop_resize(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, items_ptr, n_items,
-                                       patch_w, patch_h, out_ptr, stream), "usdu_tile_crop_resize")
+                                       patch_w, patch_h, out_ptr, flags, stream), "usdu_tile_crop_resize")
 
 
 def tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_ptr, n_items, cover_ptr, patch_w,
-               patch_h, src_ptr, src_is_u8, stream):
+               patch_h, src_ptr, src_is_u8, flags, stream):
     _check(lib().usdu_tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_ptr, n_items,
-                                 cover_ptr, patch_w, patch_h, src_ptr, int(src_is_u8), stream), "usdu_tile_blend")
+                                 cover_ptr, patch_w, patch_h, src_ptr, int(src_is_u8), flags, stream), "usdu_tile_blend")

@@ -77,7 +77,7 @@ int usdu_resample_ksize(int in_size, int out_size) {
 int64_t usdu_resample_table_words(int in_size, int out_size) {
     int ks = usdu_resample_ksize(in_size, out_size);
     if (ks < 0) return ks;
-    return (int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks);
+    return (int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks) + (int64_t)out_size * USDU_PACKED_ROW;
 }
 
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
@@ -92,7 +92,7 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
     table[0] = in_size;
     table[1] = out_size;
     table[2] = ksize;
-    table[3] = 0;
+    for (int i = 3; i < USDU_TAB_HEADER; ++i) table[i] = 0;
     int32_t* bounds = table + USDU_TAB_HEADER;
     int32_t* kk = bounds + 2 * (int64_t)out_size;
     std::vector<double> w(ksize);
@@ -121,6 +121,45 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
         for (int x = xmax; x < ksize; x++) k[x] = 0;
         bounds[xx * 2 + 0] = xmin;
         bounds[xx * 2 + 1] = xmax;
+    }
+    // Packed rows for the fast kernels: {first input index, k0..k6}, usable when no output
+    // needs more than USDU_FAST_TAPS taps and any USDU_FAST_GROUP consecutive outputs read at
+    // most USDU_FAST_WINDOW consecutive inputs.
+    int32_t* packed = kk + (int64_t)out_size * ksize;
+    int tmax = 0, span = 0;
+    for (int xx = 0; xx < out_size; xx++) {
+        if (bounds[xx * 2 + 1] > tmax) tmax = bounds[xx * 2 + 1];
+        int last = xx + USDU_FAST_GROUP - 1 < out_size ? xx + USDU_FAST_GROUP - 1 : out_size - 1;
+        int sp = bounds[last * 2] + USDU_FAST_TAPS - bounds[xx * 2];
+        if (sp > span) span = sp;
+    }
+    table[3] = tmax;
+    table[5] = span;
+    const bool fast = tmax <= USDU_FAST_TAPS && span <= USDU_FAST_WINDOW;
+    table[4] = fast ? (int32_t)(packed - table) : 0;
+    for (int xx = 0; xx < out_size; xx++) {
+        int32_t* r = packed + (int64_t)xx * USDU_PACKED_ROW;
+        r[0] = bounds[xx * 2];
+        for (int t = 0; t < USDU_FAST_TAPS; ++t)
+            r[1 + t] = (fast && t < bounds[xx * 2 + 1]) ? kk[(int64_t)xx * ksize + t] : 0;
+    }
+    return USDU_OK;
+}
+
+int usdu_build_identity_table(int size, int32_t* table) {
+    USDU_REQUIRE(table != nullptr && size > 0, "usdu_build_identity_table: bad arguments");
+    // Pillow skips a pass whose axis keeps its size (Resample.c ImagingResampleInner); one tap
+    // of weight 2^22 reproduces that exactly: (v * 2^22 + 2^21) >> 22 == v.
+    table[0] = size; table[1] = size; table[2] = 1; table[3] = 1;
+    table[4] = USDU_TAB_HEADER + 3 * size; table[5] = USDU_FAST_GROUP - 1 + USDU_FAST_TAPS; table[6] = 0; table[7] = 0;
+    int32_t* bounds = table + USDU_TAB_HEADER;
+    int32_t* kk = bounds + 2 * (int64_t)size;
+    int32_t* packed = kk + size;
+    for (int i = 0; i < size; ++i) {
+        bounds[2 * i] = i; bounds[2 * i + 1] = 1; kk[i] = 1 << usdu::kPrecisionBits;
+        int32_t* r = packed + (int64_t)i * USDU_PACKED_ROW;
+        r[0] = i; r[1] = 1 << usdu::kPrecisionBits;
+        for (int t = 1; t < USDU_FAST_TAPS; ++t) r[1 + t] = 0;
     }
     return USDU_OK;
 }

@@ -417,6 +417,14 @@ static int smem_optin(const void* fn, size_t bytes) {
 
 }  // namespace usdu
 
+namespace usdu { namespace fast {
+int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
+                const int32_t* items, int n_items, int patch_w, int patch_h, float* out, cudaStream_t st);
+int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
+                 const uint8_t* mask_pool, const int32_t* items, int n_items, const int32_t* cover, int patch_w,
+                 int patch_h, const void* src, int src_is_u8, cudaStream_t st);
+} }
+
 using namespace usdu;
 
 extern "C" {
@@ -543,12 +551,18 @@ int usdu_build_feather_masks(const int32_t* specs_host, int n_specs, uint8_t* ma
 
 int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
                           const int32_t* tiles_dev, const int32_t* tabs_dev, const int32_t* items_dev,
-                          int n_items, int patch_w, int patch_h, float* out_dev, void* stream) {
+                          int n_items, int patch_w, int patch_h, float* out_dev, int flags, void* stream) {
     USDU_REQUIRE(canvas_dev && tiles_dev && items_dev && out_dev, "usdu_tile_crop_resize: null pointer");
     USDU_REQUIRE(B > 0 && H > 0 && W > 0 && n_items >= 0, "usdu_tile_crop_resize: bad shape");
     USDU_REQUIRE(B <= 65535, "usdu_tile_crop_resize: batch %d exceeds grid.y limit", B);
     USDU_REQUIRE(patch_w > 0 && patch_h > 0, "usdu_tile_crop_resize: patch capacity must be positive");
     if (n_items == 0) return USDU_OK;
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_crop_resize: pitch must be >= 3*W and a multiple of 16");
+    if (flags & USDU_FLAG_FAST) {
+        USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: fast path needs tables");
+        return fast::launch_crop(canvas_dev, B, H, W, pitch, tiles_dev, tabs_dev, items_dev, n_items, patch_w, patch_h,
+                                 out_dev, (cudaStream_t)stream);
+    }
     const int in_pitch = (patch_w * 3 + 15) / 16 * 16;
     const size_t smem = (size_t)patch_h * in_pitch + (size_t)patch_h * BW * 3;
     int s = smem_optin((const void*)crop_resize_kernel, smem);
@@ -562,13 +576,20 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
 int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, const int32_t* tiles_dev,
                     const int32_t* tabs_dev, const uint8_t* mask_pool_dev, const int32_t* items_dev,
                     int n_items, const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
-                    int src_is_u8, void* stream) {
+                    int src_is_u8, int flags, void* stream) {
     USDU_REQUIRE(canvas_dev && tiles_dev && mask_pool_dev && items_dev && cover_dev && src_dev,
                  "usdu_tile_blend: null pointer");
     USDU_REQUIRE(B > 0 && H > 0 && W > 0 && n_items >= 0, "usdu_tile_blend: bad shape");
     USDU_REQUIRE(B <= 65535, "usdu_tile_blend: batch %d exceeds grid.y limit", B);
     USDU_REQUIRE(patch_w > 0 && patch_h > 0, "usdu_tile_blend: patch capacity must be positive");
     if (n_items == 0) return USDU_OK;
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_blend: pitch must be >= 3*W and a multiple of 16");
+    if (flags & USDU_FLAG_FAST) {
+        USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: fast path needs tables");
+        USDU_REQUIRE(((uintptr_t)src_dev & 15) == 0, "usdu_tile_blend: src must be 16-byte aligned");
+        return fast::launch_blend(canvas_dev, B, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, n_items,
+                                  cover_dev, patch_w, patch_h, src_dev, src_is_u8, (cudaStream_t)stream);
+    }
     const int in_pitch = (patch_w * 3 + 15) / 16 * 16;
     const size_t smem = (size_t)BH * BW * 3 + (size_t)patch_h * BW * 3 + (size_t)patch_h * in_pitch;
     const void* fn = src_is_u8 ? (const void*)blend_kernel<true> : (const void*)blend_kernel<false>;

@@ -29,6 +29,45 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelProfile:
+    """Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline).
+    Usage: prof = KernelProfile(); engine.PROFILE = prof; ...; prof.summary()."""
+
+    def __init__(self):
+        self.rec = []   # (name, ev0, ev1, algorithmic bytes)
+
+    def launch(self, name: str, nbytes: int, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.rec.append((name, e0, e1, nbytes))
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, nb in self.rec:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nb
+        for d in out.values():
+            d["gbps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+            d["avg_us"] = d["ms"] * 1e3 / max(d["launches"], 1)
+        return out
+
+
+PROFILE: Optional[KernelProfile] = None
+FORCE_GENERIC = False     # tests: run the generic (any-scale) kernels even when the fast ones apply
+
+
+def _launch(name: str, nbytes: int, fn):
+    if PROFILE is not None:
+        PROFILE.launch(name, nbytes, fn)
+    else:
+        fn()
+
+
 class DevicePlan:
     """Plan tables resident on one device (+ the feather templates, built there)."""
 
@@ -87,6 +126,7 @@ class Canvas:
         self.buf = torch.empty((B, self.plan.H, self.pitch), dtype=torch.uint8, device=dplan.device)
         self.launches = 0
         self.algo_bytes = 0
+        self.flags = nat.FLAG_FAST if (self.plan.fast and not FORCE_GENERIC) else 0
 
     # Q0 (single_gpu.py:30-32)
     def load(self, image: torch.Tensor):
@@ -95,7 +135,9 @@ class Canvas:
         if tuple(image.shape) != (self.B, p.H, p.W, 3) or image.dtype != torch.float32:
             raise ValueError(f"image must be float32 [{self.B},{p.H},{p.W},3], got {image.dtype} {tuple(image.shape)}")
         image = image.contiguous()
-        nat.quantize_canvas(image.data_ptr(), self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, _stream_ptr())
+        _launch("quantize", self.B * p.H * p.W * 15,
+                lambda: nat.quantize_canvas(image.data_ptr(), self.buf.data_ptr(), self.B, p.H, p.W, self.pitch,
+                                            _stream_ptr()))
         self.launches += 1
         return self
 
@@ -107,7 +149,9 @@ class Canvas:
     def result(self) -> torch.Tensor:
         p = self.plan
         out = torch.empty((self.B, p.H, p.W, 3), dtype=torch.float32, device=self.buf.device)
-        nat.dequantize_canvas(self.buf.data_ptr(), out.data_ptr(), self.B, p.H, p.W, self.pitch, _stream_ptr())
+        _launch("dequantize", self.B * p.H * p.W * 15,
+                lambda: nat.dequantize_canvas(self.buf.data_ptr(), out.data_ptr(), self.B, p.H, p.W, self.pitch,
+                                              _stream_ptr()))
         self.launches += 1
         return out
 
@@ -125,9 +169,11 @@ class Canvas:
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("crop: `out` too small or wrong dtype/device")
         p = self.plan
-        nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
-                             self.dp.tabs.data_ptr(), items.data_ptr(), items.shape[0], wl.patch_w, wl.patch_h,
-                             out.data_ptr(), _stream_ptr())
+        _launch("crop_resize", wl.algo_bytes * self.B,
+                lambda: nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch,
+                                             self.dp.tiles.data_ptr(), self.dp.tabs.data_ptr(), items.data_ptr(),
+                                             items.shape[0], wl.patch_w, wl.patch_h, out.data_ptr(), self.flags,
+                                             _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
         return out, offs
@@ -146,9 +192,11 @@ class Canvas:
             return
         p = self.plan
         src = src.contiguous()
-        nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
-                       self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(), items.shape[0],
-                       cover.data_ptr(), wl.patch_w, wl.patch_h, src.data_ptr(), src_u8, _stream_ptr())
+        _launch("blend", wl.algo_bytes * self.B,
+                lambda: nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
+                                       self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(),
+                                       items.shape[0], cover.data_ptr(), wl.patch_w, wl.patch_h, src.data_ptr(),
+                                       src_u8, self.flags, _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
 

@@ -136,6 +136,7 @@ class Plan:
     mask_pool_bytes: int = 0
     mask_class: List[int] = field(default_factory=list)
     neighbors: List[List[int]] = field(default_factory=list)   # overlapping windows, any order
+    fast: bool = True                     # every table has packed rows -> register-window kernels
     _tab_off: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_span: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
 
@@ -156,24 +157,23 @@ class Plan:
         return p
 
     def _table(self, n_in: int, n_out: int) -> int:
-        if n_in == n_out:
-            return -1
         key = (n_in, n_out)
         if key not in self._tab_off:
-            tab = nat.build_resample_table(n_in, n_out)
+            # an axis that keeps its size gets a one-tap identity table (Pillow skips the pass)
+            tab = nat.build_identity_table(n_in) if n_in == n_out else nat.build_resample_table(n_in, n_out)
+            if tab[4] == 0:
+                self.fast = False
             off = 0 if self.tabs is None else int(self.tabs.shape[0])
             self.tabs = tab if self.tabs is None else np.concatenate([self.tabs, tab])
             self._tab_off[key] = off
             b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
-            self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + b[:, 1]], 1)   # [lo, hi) per output
+            self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], 7)], 1)   # [lo, hi) per output (>= 7 taps staged)
         return self._tab_off[key]
 
     def _build_tables(self):
         for t in self.tiles:
             self._table(t.ew, t.pw), self._table(t.eh, t.ph)
             self._table(t.pw, t.ew), self._table(t.ph, t.eh)
-        if self.tabs is None:
-            self.tabs = np.zeros(nat.TAB_HEADER, dtype=np.int32)
 
     def _ramp(self) -> int:
         """Pixels beyond the rectangle that the blurred mask can be non-zero (3 box
@@ -210,6 +210,21 @@ class Plan:
         if self.mask_pool_bytes >= 2 ** 31:
             raise ValueError("feather templates exceed 2 GiB")
 
+    def opaque_core(self, t: Tile) -> Tuple[int, int, int, int]:
+        """Window-relative box inside which the feather alpha is exactly 255: the rectangle
+        shrunk by the ramp, except on sides where the rectangle touches the canvas border
+        (edge replication keeps the mask at 255 there)."""
+        ext = self._ramp()
+        fx0 = t.bx1 if t.bx1 == 0 else t.bx1 + ext
+        fy0 = t.by1 if t.by1 == 0 else t.by1 + ext
+        fx1 = t.bx2 if t.bx2 == self.W else t.bx2 - ext
+        fy1 = t.by2 if t.by2 == self.H else t.by2 - ext
+        fx0, fy0 = max(fx0, t.x1), max(fy0, t.y1)
+        fx1, fy1 = min(fx1, t.x2), min(fy1, t.y2)
+        if fx1 <= fx0 or fy1 <= fy0:
+            return (0, 0, 0, 0)
+        return (fx0 - t.x1, fy0 - t.y1, fx1 - t.x1, fy1 - t.y1)
+
     def support(self, t: Tile) -> Tuple[int, int, int, int]:
         """Window-relative bbox outside which the feather alpha is exactly 0."""
         ext = self._ramp()
@@ -226,6 +241,7 @@ class Plan:
             r[nat.T_TAB_CROP_H], r[nat.T_TAB_CROP_V] = self._table(t.ew, t.pw), self._table(t.eh, t.ph)
             r[nat.T_TAB_BLEND_H], r[nat.T_TAB_BLEND_V] = self._table(t.pw, t.ew), self._table(t.ph, t.eh)
             r[nat.T_SUP_X0:nat.T_SUP_Y1 + 1] = self.support(t)
+            r[nat.T_FULL_X0:nat.T_FULL_Y1 + 1] = self.opaque_core(t)
         self.tile_desc = d
 
     def _build_neighbors(self):
@@ -321,8 +337,6 @@ class Plan:
 
     def _span_max(self, n_in: int, n_out: int, block: int, aligned: bool) -> int:
         """Largest input extent read by `block` consecutive outputs of an axis."""
-        if n_in == n_out:
-            return min(block, n_out)
         sp = self._tab_span[(n_in, n_out)]
         starts = np.arange(0, n_out, block) if aligned else np.arange(0, n_out)
         ends = np.minimum(starts + block, n_out) - 1

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 1
+#define USDU_ABI_VERSION 2
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -46,7 +46,7 @@ typedef enum usdu_status {
  * Tile descriptor: USDU_TILE_WORDS int32 per tile position (geometry is identical for all
  * frames of a batch, upscale/tile_ops.py:108-138).
  */
-#define USDU_TILE_WORDS 16
+#define USDU_TILE_WORDS 24
 #define USDU_T_X1 0          /* crop window origin on the canvas */
 #define USDU_T_Y1 1
 #define USDU_T_EW 2          /* crop window ("extracted") size */
@@ -55,7 +55,7 @@ typedef enum usdu_status {
 #define USDU_T_PH 5
 #define USDU_T_MASK_OFF 6    /* byte offset of this tile's feather template in the mask pool */
 #define USDU_T_MASK_PITCH 7  /* bytes per template row (>= EW) */
-#define USDU_T_TAB_CROP_H 8  /* int32 offset of a resample table in the table pool, -1 = identity */
+#define USDU_T_TAB_CROP_H 8  /* int32 offset of a resample table in the table pool (an identity table when the axis keeps its size; -1 is accepted by the generic kernels only) */
 #define USDU_T_TAB_CROP_V 9  /*   crop:  EW->PW (H), EH->PH (V) */
 #define USDU_T_TAB_BLEND_H 10 /*  blend: PW->EW (H), PH->EH (V) */
 #define USDU_T_TAB_BLEND_V 11
@@ -63,13 +63,24 @@ typedef enum usdu_status {
 #define USDU_T_SUP_Y0 13
 #define USDU_T_SUP_X1 14
 #define USDU_T_SUP_Y1 15
+#define USDU_T_FULL_X0 16    /* window-relative box inside which the template alpha is exactly 255 */
+#define USDU_T_FULL_Y0 17
+#define USDU_T_FULL_X1 18
+#define USDU_T_FULL_Y1 19    /* words 20..23 reserved (0) */
 
 /* Resample table at int32 offset o of the table pool:
- *   [o+0]=in_size [o+1]=out_size [o+2]=ksize [o+3]=0
- *   [o+4 ...]            bounds: out_size x {first input index, tap count}
- *   [o+4+2*out_size ...] kk: out_size x ksize coefficients, 22-bit fixed point
+ *   [o+0]=in_size [o+1]=out_size [o+2]=ksize [o+3]=max taps actually used by any output
+ *   [o+4]=offset (from o) of the packed rows, 0 when the fast kernels cannot use this table
+ *   [o+5]=max inputs read by USDU_FAST_GROUP consecutive outputs  [o+6],[o+7]=0
+ *   [o+8 ...]            bounds: out_size x {first input index, tap count}
+ *   [o+8+2*out_size ...] kk: out_size x ksize coefficients, 22-bit fixed point
+ *   then packed rows: out_size x USDU_PACKED_ROW = {first input index, k0..k6}
  * (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc.) */
-#define USDU_TAB_HEADER 4
+#define USDU_TAB_HEADER 8
+#define USDU_PACKED_ROW 8
+#define USDU_FAST_TAPS 7     /* taps per output handled by the fast kernels */
+#define USDU_FAST_GROUP 8    /* consecutive outputs one thread computes from one register window */
+#define USDU_FAST_WINDOW 16  /* inputs held in that window */
 
 /* Crop work item: one BHxBW block of one tile's processing-size output. */
 #define USDU_CROP_ITEM_WORDS 6
@@ -108,10 +119,18 @@ int usdu_resample_ksize(int in_size, int out_size);
 int64_t usdu_resample_table_words(int in_size, int out_size);
 /* fill `table` (host, usdu_resample_table_words() int32) */
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table);
+/* table of an axis that keeps its size (size -> size): one tap of weight 2^22;
+ * USDU_TAB_HEADER + size * (3 + USDU_PACKED_ROW) int32 */
+int usdu_build_identity_table(int size, int32_t* table);
 /* ImageFilter.GaussianBlur(radius) -> extended-box parameters (BoxBlur.c, 3 passes) */
 int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw);
 
 /* ---- device kernels ----------------------------------------------------------------- */
+/* `flags` of the two tile kernels: USDU_FLAG_FAST selects the register-window kernels
+ * (usdu_fast.cu); the caller may set it only when every table referenced by the launch has
+ * packed rows (table word 4 != 0) and no table offset is -1.  Without it the generic
+ * kernels run (any scale, any tap count). */
+#define USDU_FLAG_FAST 1
 /* Q0: canvas_u8[b][y][x*3+c] = (uint8)(255.f * img[b][y][x][c])   (utils/image.py:8-10)
  * pitch = bytes per canvas row (>= 3*W, multiple of 16); frame stride = H*pitch. */
 int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W,
@@ -137,7 +156,7 @@ int usdu_build_feather_masks(const int32_t* specs_host, int n_specs, uint8_t* ma
 int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
                           const int32_t* tiles_dev, const int32_t* tabs_dev,
                           const int32_t* items_dev, int n_items, int patch_w, int patch_h,
-                          float* out_dev, void* stream);
+                          float* out_dev, int flags, void* stream);
 
 /* Seam blend: for every item (canvas block) apply its cover list in order:
  * quantise (fp32 source) -> LANCZOS back to the crop size -> integer alpha composite
@@ -151,7 +170,7 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
                     const int32_t* tiles_dev, const int32_t* tabs_dev,
                     const uint8_t* mask_pool_dev, const int32_t* items_dev, int n_items,
                     const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
-                    int src_is_u8, void* stream);
+                    int src_is_u8, int flags, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -28,6 +28,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+@pytest.fixture(params=["fast", "generic"], autouse=True)
+def kernel_path(request):
+    """Every test runs twice: with the register-window kernels (when the plan allows them)
+    and with the generic any-scale kernels forced."""
+    engine.FORCE_GENERIC = request.param == "generic"
+    yield request.param
+    engine.FORCE_GENERIC = False
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 33, 50), (1, 7, 1021), (1, 540, 960)])
 def test_quantize_dequantize(B, H, W):
     rng = np.random.default_rng(0)
@@ -221,6 +230,7 @@ def test_full_size_properties_cfg2():
     b = engine.upscale_single(img, den, 512, 512, 32, 8, True)
     assert torch.equal(a, b)
     assert st["tiles"] == 135 and st["waves"] == 31
+    assert planner.get_plan(W, H, 512, 512, 32, 8, True).fast
     part = a[:, 1000:1400].cpu().numpy()                            # output values are k/255 (IEEE division)
     assert np.array_equal(orc.dequantize_u8(np.round(part * 255).astype(np.uint8)), part)
     # spot-check three windows of the big canvas against the oracle run on a sub-canvas is not

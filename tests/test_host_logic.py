@@ -47,16 +47,32 @@ def test_error_reporting_without_device_or_with_bad_args():
     with pytest.raises(nat.NativeError):
         nat.quantize_canvas(0, 0, 1, 1, 1, 16, 0)      # null pointers are rejected before any CUDA call
     with pytest.raises(nat.NativeError):
-        nat.tile_blend(1, 1, 8, 8, 17, 1, 1, 1, 1, 1, 1, 8, 8, 0, 0, 0)
+        nat.tile_blend(1, 1, 8, 8, 17, 1, 1, 1, 1, 1, 1, 8, 8, 0, 0, 0, 0)
 
 
 @pytest.mark.parametrize("n_in,n_out", [(576, 544), (544, 576), (320, 288), (288, 544), (100, 160), (1, 8), (2304, 1152), (37, 64)])
 def test_resample_table_equals_oracle(n_in, n_out):
     tab = nat.build_resample_table(n_in, n_out)
     bounds, kk = orc.lanczos_coeffs(n_in, n_out)
-    assert tab[0] == n_in and tab[1] == n_out and tab[2] == kk.shape[1]
-    assert np.array_equal(tab[4:4 + 2 * n_out].reshape(n_out, 2), bounds)
-    assert np.array_equal(tab[4 + 2 * n_out:].reshape(n_out, -1), kk)
+    ks = kk.shape[1]
+    H = nat.TAB_HEADER
+    assert tab[0] == n_in and tab[1] == n_out and tab[2] == ks
+    assert np.array_equal(tab[H:H + 2 * n_out].reshape(n_out, 2), bounds)
+    assert np.array_equal(tab[H + 2 * n_out:H + 2 * n_out + n_out * ks].reshape(n_out, ks), kk)
+    assert tab[3] == bounds[:, 1].max()
+    if tab[4]:                                           # packed rows: {first, k0..k6}, zero padded
+        rows = tab[tab[4]:tab[4] + 8 * n_out].reshape(n_out, 8)
+        assert np.array_equal(rows[:, 0], bounds[:, 0])
+        assert np.array_equal(rows[:, 1:], kk[:, :7] if ks >= 7 else np.pad(kk, ((0, 0), (0, 7 - ks))))
+        assert tab[3] <= 7 and tab[5] <= 16
+    else:
+        assert tab[3] > 7 or tab[5] > 16
+
+
+def test_identity_table():
+    tab = nat.build_identity_table(5)
+    rows = tab[tab[4]:].reshape(5, 8)
+    assert list(rows[:, 0]) == [0, 1, 2, 3, 4] and (rows[:, 1] == 1 << 22).all() and not rows[:, 2:].any()
 
 
 def test_box_blur_params_equal_oracle_for_every_radius():
@@ -125,6 +141,8 @@ def test_mask_classes_and_worklists():
         z = ma.copy()
         z[sy0:sy1, sx0:sx1] = 0
         assert not z.any()
+        fx0, fy0, fx1, fy1 = p.opaque_core(a)             # ... and exactly 255 inside the opaque core
+        assert fx1 > fx0 and (ma[fy0:fy1, fx0:fx1] == 255).all()
     ids = list(range(135))
     wl, offs, total = p.crop_worklist(ids, 1)
     assert total == 135 * 544 * 544 * 3
