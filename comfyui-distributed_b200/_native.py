@@ -31,6 +31,8 @@ COVER_WORDS = 4
 MASK_WORDS = 16
 BLOCK_W = 64
 BLOCK_H = 32
+FAST_BLOCK_W = 128
+FAST_BLOCK_H = 32
 
 
 class NativeError(RuntimeError):

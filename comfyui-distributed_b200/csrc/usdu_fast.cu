@@ -114,41 +114,43 @@ struct CropEpilogue {
     int64_t row_pitch;   // floats per output row
     int oh, ow3;
     const float* lut;
-    __device__ __forceinline__ void row(int r, int strip, uint32_t s0, uint32_t s1) {
-        if (r < oh && 2 * strip < ow3) {   // ow3 is even (pw % 8 == 0)
-            float2 o;
-            o.x = lut[s0];
-            o.y = lut[s1];
-            __stcs(reinterpret_cast<float2*>(dst + (int64_t)r * row_pitch + 2 * strip), o);
+    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
+        if (r < oh && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
+            float4 o;
+            o.x = lut[s[0]]; o.y = lut[s[1]]; o.z = lut[s[2]]; o.w = lut[s[3]];
+            __stcs(reinterpret_cast<float4*>(dst + (int64_t)r * row_pitch + 4 * strip), o);
         }
     }
 };
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
                  const int32_t* __restrict__ tabs, const int32_t* __restrict__ items, float* __restrict__ out,
                  int patch_w, int patch_h) {
     extern __shared__ __align__(16) uint8_t smem[];
-    float* lut = reinterpret_cast<float*>(smem);
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem + 1024);
-    uint8_t* mid = smem + 1024 + in_bytes(patch_w, patch_h);
+    int32_t* rows_h = reinterpret_cast<int32_t*>(smem);
+    int32_t* rows_v = rows_h + FBW * USDU_PACKED_ROW;
+    float* lut = reinterpret_cast<float*>(smem + kRowsBytes);
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kRowsBytes + 1024);
+    uint8_t* mid = smem + kRowsBytes + 1024 + in_bytes(patch_w, patch_h);
     for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8(i);
 
     const int32_t* it = items + (int64_t)blockIdx.x * USDU_CROP_ITEM_WORDS;
     const int32_t* T = tiles + (int64_t)it[0] * USDU_TILE_WORDS;
     const int b = blockIdx.y;
-    const int ox0 = it[1], oy0 = it[2];
+    const int ox0 = it[1], oy0 = it[2], bh = it[5];
     const int64_t out_off = (int64_t)(uint32_t)it[3] | ((int64_t)it[4] << 32);
     const int x1 = T[USDU_T_X1], y1 = T[USDU_T_Y1], pw = T[USDU_T_PW], ph = T[USDU_T_PH];
     const Axis ah = axis_of(tabs, T[USDU_T_TAB_CROP_H]), av = axis_of(tabs, T[USDU_T_TAB_CROP_V]);
+    stage_rows(rows_h, ah.rows, ah.n_out, ox0, FBW);
+    stage_rows(rows_v, av.rows, av.n_out, oy0, FBH);
 
     Job J;
-    J.rows_h = ah.rows; J.rows_v = av.rows; J.n_out_h = ah.n_out; J.n_out_v = av.n_out;
-    J.ox_base = ox0; J.oy_base = oy0;
+    J.rows_h = rows_h; J.rows_v = rows_v;
     J.ix0 = first_of(ah, ox0);
     J.iy0 = first_of(av, oy0);
-    const int ix1 = min(first_of(ah, ox0 + BW - 1) + TAPS, ah.n_in);
-    const int iy1 = min(first_of(av, oy0 + BH - 1) + TAPS, av.n_in);
+    const int ix1 = min(first_of(ah, ox0 + FBW - 1) + TAPS, ah.n_in);
+    const int iy1 = min(first_of(av, oy0 + bh - 1) + TAPS, av.n_in);
     J.rows_in = iy1 - J.iy0;
     J.xw = plane_words(patch_w);
 
@@ -163,8 +165,8 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch
     CropEpilogue epi;
     epi.dst = out + out_off + ((int64_t)b * ph + oy0) * pw * 3 + (int64_t)ox0 * 3;
     epi.row_pitch = (int64_t)pw * 3;
-    epi.oh = min(BH, ph - oy0);
-    epi.ow3 = min(BW, pw - ox0) * 3;
+    epi.oh = min(bh, ph - oy0);
+    epi.ow3 = min(FBW, pw - ox0) * 3;
     epi.lut = lut;
     vpass(mid, J, epi);
 }
@@ -176,8 +178,8 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch
 struct BlendOpaque {
     uint8_t* dst;        // canvas block origin
     int64_t pitch;
-    __device__ __forceinline__ void row(int r, int strip, uint32_t s0, uint32_t s1) {
-        *reinterpret_cast<uint16_t*>(dst + (int64_t)r * pitch + 2 * strip) = (uint16_t)(s0 | (s1 << 8));
+    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + 4 * strip) = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
     }
 };
 
@@ -188,41 +190,49 @@ struct BlendFeather {
     const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
     int mpitch;
     int cx0, cx1, cy0, cy1;   // sub-rect in block pixel coordinates
-    __device__ __forceinline__ void row(int r, int strip, uint32_t s0, uint32_t s1) {
+    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
         if (r < cy0 || r >= cy1) return;
-        const int col = 2 * strip;
-        const int p0 = col / 3, p1 = (col + 1) / 3;
-        const bool in0 = p0 >= cx0 && p0 < cx1, in1 = p1 >= cx0 && p1 < cx1;
-        if (!in0 && !in1) return;
+        const int col = 4 * strip;
+        const int pa = col / 3, pb = (col + 3) / 3;          // the 4 bytes touch pixels pa and pb (pb = pa or pa+1)
+        const bool ina = pa >= cx0 && pa < cx1, inb = pb >= cx0 && pb < cx1;
+        if (!ina && !inb) return;
         const uint8_t* mrow = mask + (int64_t)r * mpitch;
-        const uint32_t a0 = in0 ? __ldg(mrow + p0) : 0u;
-        const uint32_t a1 = in1 ? (p1 == p0 ? a0 : (uint32_t)__ldg(mrow + p1)) : 0u;
-        uint16_t* d = reinterpret_cast<uint16_t*>(dst + (int64_t)r * pitch + col);
-        if (a0 == 255u && a1 == 255u) {
-            *d = (uint16_t)(s0 | (s1 << 8));
+        const uint32_t aa = ina ? __ldg(mrow + pa) : 0u;
+        const uint32_t ab = inb ? (pb == pa ? aa : (uint32_t)__ldg(mrow + pb)) : 0u;
+        const int split = 3 * pb - col;                      // bytes [0, split) belong to pa, the rest to pb
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + col);
+        if (aa == 255u && ab == 255u) {
+            *d = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
             return;
         }
-        if (a0 == 0u && a1 == 0u) return;
+        if (aa == 0u && ab == 0u) return;
         const uint32_t dv = *d;
-        const uint32_t o0 = composite8(s0, dv & 0xFF, a0), o1 = composite8(s1, dv >> 8, a1);
-        *d = (uint16_t)(o0 | (o1 << 8));
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a = i < split ? aa : ab;
+            o |= composite8(s[i], (dv >> (8 * i)) & 0xFF, a) << (8 * i);
+        }
+        *d = o;
     }
 };
 
 template <bool kSrcU8>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
                   const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
                   const int32_t* __restrict__ items, const int32_t* __restrict__ cover,
                   const void* __restrict__ src_v, int patch_w, int patch_h) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem);
-    uint8_t* mid = smem + in_bytes(patch_w, patch_h);
+    int32_t* rows_h = reinterpret_cast<int32_t*>(smem);
+    int32_t* rows_v = rows_h + FBW * USDU_PACKED_ROW;
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kRowsBytes);
+    uint8_t* mid = smem + kRowsBytes + in_bytes(patch_w, patch_h);
 
     const int32_t* it = items + (int64_t)blockIdx.x * USDU_BLEND_ITEM_WORDS;
     const int b = blockIdx.y;
     const int bx0 = it[0], by0 = it[1];
-    const int bw = min(BW, W - bx0), bh = min(BH, H - by0);
+    const int bw = min(FBW, W - bx0), bh = min(FBH, H - by0);
     uint8_t* cblk = canvas + ((int64_t)b * H + by0) * pitch + (int64_t)bx0 * 3;
     const int c0 = it[2], cn = it[3];
     for (int e = 0; e < cn; ++e) {
@@ -236,16 +246,18 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, con
         const int Y0 = max(by0, y1 + T[USDU_T_SUP_Y0]), Y1 = min(by0 + bh, y1 + T[USDU_T_SUP_Y1]);
         if (X1 <= X0 || Y1 <= Y0) continue;   // uniform
         const Axis ah = axis_of(tabs, T[USDU_T_TAB_BLEND_H]), av = axis_of(tabs, T[USDU_T_TAB_BLEND_V]);
+        const int ox_base = bx0 - x1, oy_base = by0 - y1;
+        __syncthreads();   // the previous tile's passes are done with rows / in / mid
+        stage_rows(rows_h, ah.rows, ah.n_out, ox_base, FBW);
+        stage_rows(rows_v, av.rows, av.n_out, oy_base, FBH);
         Job J;
-        J.rows_h = ah.rows; J.rows_v = av.rows; J.n_out_h = ah.n_out; J.n_out_v = av.n_out;
-        J.ox_base = bx0 - x1; J.oy_base = by0 - y1;
-        J.ix0 = first_of(ah, J.ox_base);
-        J.iy0 = first_of(av, J.oy_base);
-        const int ix1 = min(first_of(ah, J.ox_base + BW - 1) + TAPS, ah.n_in);
-        const int iy1 = min(first_of(av, J.oy_base + BH - 1) + TAPS, av.n_in);
+        J.rows_h = rows_h; J.rows_v = rows_v;
+        J.ix0 = first_of(ah, ox_base);
+        J.iy0 = first_of(av, oy_base);
+        const int ix1 = min(first_of(ah, ox_base + FBW - 1) + TAPS, ah.n_in);
+        const int iy1 = min(first_of(av, oy_base + FBH - 1) + TAPS, av.n_in);
         J.rows_in = iy1 - J.iy0;
         J.xw = plane_words(patch_w);
-        __syncthreads();   // the previous tile's passes are done with in / mid
         const int lead = J.ix0 & 3;
         const int64_t frame = (int64_t)ph * pw * 3;
         const int64_t first = src_off + b * frame + ((int64_t)J.iy0 * pw + (J.ix0 - lead)) * 3;
@@ -259,8 +271,8 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, con
         hpass(in, mid, J);
         __syncthreads();
         // whole block inside the opaque core of this tile?
-        const bool opaque = bw == BW && bh == BH && bx0 >= x1 + T[USDU_T_FULL_X0] && bx0 + BW <= x1 + T[USDU_T_FULL_X1] &&
-                            by0 >= y1 + T[USDU_T_FULL_Y0] && by0 + BH <= y1 + T[USDU_T_FULL_Y1];
+        const bool opaque = bw == FBW && bh == FBH && bx0 >= x1 + T[USDU_T_FULL_X0] && bx0 + FBW <= x1 + T[USDU_T_FULL_X1] &&
+                            by0 >= y1 + T[USDU_T_FULL_Y0] && by0 + FBH <= y1 + T[USDU_T_FULL_Y1];
         if (opaque) {
             BlendOpaque epi;
             epi.dst = cblk;
@@ -271,15 +283,15 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, con
             epi.dst = cblk;
             epi.pitch = pitch;
             epi.mpitch = T[USDU_T_MASK_PITCH];
-            epi.mask = mask_pool + (int64_t)(uint32_t)T[USDU_T_MASK_OFF] + (int64_t)J.oy_base * epi.mpitch + J.ox_base;
+            epi.mask = mask_pool + (int64_t)(uint32_t)T[USDU_T_MASK_OFF] + (int64_t)oy_base * epi.mpitch + ox_base;
             epi.cx0 = X0 - bx0; epi.cx1 = X1 - bx0; epi.cy0 = Y0 - by0; epi.cy1 = Y1 - by0;
             vpass(mid, J, epi);
         }
     }
 }
 
-static size_t crop_smem(int patch_w, int patch_h) { return 1024 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
-static size_t blend_smem(int patch_w, int patch_h) { return in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t crop_smem(int patch_w, int patch_h) { return kRowsBytes + 1024 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t blend_smem(int patch_w, int patch_h) { return kRowsBytes + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
 
 static int optin(const void* fn, size_t bytes) {
     if (bytes > 227 * 1024) {

@@ -10,11 +10,11 @@
 // uniform branch into straight-line code with compile-time register indices: ~1.3
 // instructions per tap.
 //
-//   H pass  lanes = (row pair, channel), one warp per group of 8 output pixels.  Input is
+//   H pass  lanes = (group of 4 rows, channel), one warp per group of 8 output pixels.  Input is
 //           staged PLANAR and ROW-PACKED: word(g, c, x) = bytes of rows 4g..4g+3 of channel
 //           c at pixel x, so a window is 16 consecutive words and one PRMT yields a row's
 //           byte; no alignment fix-ups.
-//   V pass  lanes = 2-byte column strips, one warp per group of 8 output rows, input is the
+//   V pass  lanes = 4-byte column strips, one warp per group of 8 output rows, input is the
 //           H-pass result `mid` (row-major u8, pixel interleaved, block pixel coordinates).
 //
 // Arithmetic is Pillow's (Resample.c): acc = 2^21 + sum in*k ; out = clip8(acc >> 22), with a
@@ -26,11 +26,13 @@ namespace usdu {
 namespace fast {
 
 constexpr int kT = 128;                    // threads per CTA (4 warps)
+constexpr int FBW = USDU_FAST_BLOCK_W;     // 128-pixel wide blocks
+constexpr int FBH = USDU_FAST_BLOCK_H;     // up to 32 rows
 constexpr int TAPS = USDU_FAST_TAPS;       // 7
 constexpr int GROUP = USDU_FAST_GROUP;     // 8 outputs per window
 constexpr int WIN = USDU_FAST_WINDOW;      // 16 inputs per window
-constexpr int NCASE = WIN - TAPS + 1;      // 10 window offsets
-constexpr int MID_PITCH = BW * 3 + 4;      // 196 bytes: rows 4 banks apart -> conflict-free byte stores
+constexpr int R = 4;                       // independent lines (rows / byte columns) per thread
+constexpr int MID_PITCH = FBW * 3 + 4;     // 388 bytes: 4 consecutive rows land 4 banks apart
 
 struct PackedRow {  // one output of an axis: first input index + 7 coefficients (32 bytes)
     int first;
@@ -46,40 +48,38 @@ __device__ __forceinline__ PackedRow load_row(const int32_t* rows, int idx) {
     return r;
 }
 
-template <int D, int R>
+template <int D>
 __device__ __forceinline__ void dot_at(const int (&v)[WIN][R], const PackedRow& row, int (&acc)[R]) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int a = 1 << (kPrecisionBits - 1);
+    for (int r = 0; r < R; ++r) acc[r] = 1 << (kPrecisionBits - 1);
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) a += v[D + t][r] * row.k[t];
-        acc[r] = a;
+    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += v[D + t][r] * row.k[t];
     }
 }
 
-// acc[r] = 2^21 + sum_t v[d + t][r] * k[t]   with d warp-uniform in [0, NCASE)
-template <int R>
+// acc[r] = 2^21 + sum_t v[d + t][r] * k[t]   with d warp-uniform in [0, WIN - TAPS]
 __device__ __forceinline__ void dot_window(const int (&v)[WIN][R], const PackedRow& row, int d, int (&acc)[R]) {
+    __builtin_assume(d >= 0 && d <= WIN - TAPS);
     switch (d) {
-        case 0: dot_at<0, R>(v, row, acc); break;
-        case 1: dot_at<1, R>(v, row, acc); break;
-        case 2: dot_at<2, R>(v, row, acc); break;
-        case 3: dot_at<3, R>(v, row, acc); break;
-        case 4: dot_at<4, R>(v, row, acc); break;
-        case 5: dot_at<5, R>(v, row, acc); break;
-        case 6: dot_at<6, R>(v, row, acc); break;
-        case 7: dot_at<7, R>(v, row, acc); break;
-        case 8: dot_at<8, R>(v, row, acc); break;
-        default: dot_at<9, R>(v, row, acc); break;
+        case 0: dot_at<0>(v, row, acc); break;
+        case 1: dot_at<1>(v, row, acc); break;
+        case 2: dot_at<2>(v, row, acc); break;
+        case 3: dot_at<3>(v, row, acc); break;
+        case 4: dot_at<4>(v, row, acc); break;
+        case 5: dot_at<5>(v, row, acc); break;
+        case 6: dot_at<6>(v, row, acc); break;
+        case 7: dot_at<7>(v, row, acc); break;
+        case 8: dot_at<8>(v, row, acc); break;
+        case 9: dot_at<9>(v, row, acc); break;
     }
 }
 
 // Geometry of one (block, tile) resampling job, all warp-uniform.
 struct Job {
-    const int32_t* rows_h;  // packed rows of the horizontal axis (global)
-    const int32_t* rows_v;
-    int n_out_h, n_out_v;   // output sizes of the two axes (for clamping)
-    int ox_base, oy_base;   // output index of block pixel (0,0): out = base + block coordinate (may be < 0)
+    const int32_t* rows_h;  // shared memory: packed rows of block pixel columns 0..FBW-1 (already clamped)
+    const int32_t* rows_v;  // shared memory: packed rows of block rows 0..FBH-1
     int ix0, iy0;           // first input column / row held in shared memory
     int rows_in;            // staged input rows
     int xw;                 // words per (g, c) plane row of `in`
@@ -87,75 +87,80 @@ struct Job {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// Copy the packed rows of outputs base .. base+count-1 (clamped to the axis) into shared memory.
+__device__ __forceinline__ void stage_rows(int32_t* dst, const int32_t* rows, int n_out, int base, int count) {
+    for (int i = threadIdx.x; i < count * 2; i += kT) {
+        const int o = clampi(base + (i >> 1), 0, n_out - 1);
+        reinterpret_cast<int4*>(dst)[i] = __ldg(reinterpret_cast<const int4*>(rows + (size_t)o * USDU_PACKED_ROW) + (i & 1));
+    }
+}
+
 // ---- H pass: in (planar, row packed) -> mid[row][block px * 3 + c] ----------------------
+// lanes = (row group g of 4 rows, channel c); one warp-task per group of 8 output pixels.
 __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const Job& J) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int npairs = (J.rows_in + 1) >> 1;
-    const int units = npairs * 3;
+    const int units = ((J.rows_in + 3) >> 2) * 3;
     const int parts = (units + 31) >> 5;            // warps needed per pixel group
-    const int ntask = (BW / GROUP) * parts;
+    const int ntask = (FBW / GROUP) * parts;
     for (int task = warp; task < ntask; task += kT / 32) {
         const int q = task / parts, part = task - q * parts;
         const int u = part * 32 + lane;
         const bool live = u < units;
         const int uu = live ? u : 0;
-        const int pair = uu / 3, c = uu - pair * 3;
-        const int g = pair >> 1, half = pair & 1;
-        const int x_first = clampi(J.ox_base + q * GROUP, 0, J.n_out_h - 1);
-        const int base = __ldg(J.rows_h + (size_t)x_first * USDU_PACKED_ROW);   // uniform
-        const uint32_t* w = in + (size_t)(g * 3 + c) * J.xw + (base - J.ix0);
-        int v[WIN][2];
-        const uint32_t sel0 = 0x4440u + 2 * half, sel1 = 0x4441u + 2 * half;
+        const int g = uu / 3, c = uu - g * 3;
+        const int base = J.rows_h[(q * GROUP) * USDU_PACKED_ROW];                // uniform
+        const uint32_t* w = in + (size_t)uu * J.xw + (base - J.ix0);
+        int v[WIN][R];
 #pragma unroll
         for (int j = 0; j < WIN; ++j) {
             const uint32_t word = w[j];
-            v[j][0] = __byte_perm(word, 0, sel0);
-            v[j][1] = __byte_perm(word, 0, sel1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[j][r] = __byte_perm(word, 0, 0x4440 + r);
         }
-        uint8_t* o = mid + (size_t)(4 * g + 2 * half) * MID_PITCH + (q * GROUP) * 3 + c;
+        uint8_t* o = mid + (size_t)(4 * g) * MID_PITCH + (q * GROUP) * 3 + c;
 #pragma unroll 1
         for (int p = 0; p < GROUP; ++p) {
-            const int xx = clampi(J.ox_base + q * GROUP + p, 0, J.n_out_h - 1);
-            const PackedRow row = load_row(J.rows_h, xx);
-            int acc[2];
-            dot_window<2>(v, row, row.first - base, acc);
+            const PackedRow row = load_row(J.rows_h, q * GROUP + p);
+            int acc[R];
+            dot_window(v, row, row.first - base, acc);
             if (live) {
-                o[p * 3] = (uint8_t)clip8(acc[0] >> kPrecisionBits);
-                o[p * 3 + MID_PITCH] = (uint8_t)clip8(acc[1] >> kPrecisionBits);
+#pragma unroll
+                for (int r = 0; r < R; ++r) o[p * 3 + r * MID_PITCH] = (uint8_t)clip8(acc[r] >> kPrecisionBits);
             }
         }
     }
 }
 
 // ---- V pass: mid -> S values, handed to an epilogue -------------------------------------
-// Epilogue::row(int block_row, int strip, uint32_t s0, uint32_t s1): the two resampled bytes
-// of byte columns 2*strip, 2*strip+1 of block row `block_row`.
+// lanes = 4-byte column strips; one warp-task per (group of 8 output rows, third of the strips).
+// Epilogue::row(int block_row, int strip, const uint32_t (&s)[4]): the resampled bytes of byte
+// columns 4*strip .. 4*strip+3 of block row `block_row`.
 template <class Epilogue>
 __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const Job& J, Epilogue& epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int STRIPS = BW * 3 / 2;              // 96 two-byte strips
-    constexpr int PARTS = STRIPS / 32;              // 3 warps per row group
-    constexpr int NTASK = (BH / GROUP) * PARTS;     // 12
+    constexpr int PARTS = FBW * 3 / 4 / 32;         // 3 warps per row group
+    constexpr int NTASK = (FBH / GROUP) * PARTS;    // 12
     for (int task = warp; task < NTASK; task += kT / 32) {
         const int rg = task / PARTS, part = task - rg * PARTS;
         const int strip = part * 32 + lane;
-        const int y_first = clampi(J.oy_base + rg * GROUP, 0, J.n_out_v - 1);
-        const int base = __ldg(J.rows_v + (size_t)y_first * USDU_PACKED_ROW);   // uniform
-        const uint8_t* m = mid + (size_t)(base - J.iy0) * MID_PITCH + 2 * strip;
-        int v[WIN][2];
+        const int base = J.rows_v[(rg * GROUP) * USDU_PACKED_ROW];                // uniform
+        const uint8_t* m = mid + (size_t)(base - J.iy0) * MID_PITCH + 4 * strip;
+        int v[WIN][R];
 #pragma unroll
         for (int j = 0; j < WIN; ++j) {
-            const uint32_t word = *reinterpret_cast<const uint16_t*>(m + (size_t)j * MID_PITCH);
-            v[j][0] = word & 0xFF;
-            v[j][1] = word >> 8;
+            const uint32_t word = *reinterpret_cast<const uint32_t*>(m + (size_t)j * MID_PITCH);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[j][r] = __byte_perm(word, 0, 0x4440 + r);
         }
 #pragma unroll 1
         for (int p = 0; p < GROUP; ++p) {
-            const int yy = clampi(J.oy_base + rg * GROUP + p, 0, J.n_out_v - 1);
-            const PackedRow row = load_row(J.rows_v, yy);
-            int acc[2];
-            dot_window<2>(v, row, row.first - base, acc);
-            epi.row(rg * GROUP + p, strip, clip8(acc[0] >> kPrecisionBits), clip8(acc[1] >> kPrecisionBits));
+            const PackedRow row = load_row(J.rows_v, rg * GROUP + p);
+            int acc[R];
+            dot_window(v, row, row.first - base, acc);
+            uint32_t s[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) s[r] = clip8(acc[r] >> kPrecisionBits);
+            epi.row(rg * GROUP + p, strip, s);
         }
     }
 }
@@ -169,6 +174,7 @@ __host__ __device__ inline size_t in_bytes(int patch_w, int patch_h) {
 __host__ __device__ inline size_t mid_bytes(int patch_h) {
     return ((size_t)(patch_h + WIN + 4) * MID_PITCH + 15) / 16 * 16;
 }
+constexpr size_t kRowsBytes = (size_t)(FBW + FBH) * USDU_PACKED_ROW * 4;   // staged coefficient rows
 
 }  // namespace fast
 }  // namespace usdu

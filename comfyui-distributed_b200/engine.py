@@ -100,17 +100,17 @@ class DevicePlan:
         cover = torch.from_numpy(wl.cover).to(self.device) if wl.cover is not None else None
         return items, cover
 
-    def crop_list(self, tile_ids: Tuple[int, ...], B: int):
-        key = ("crop", tile_ids, B)
+    def crop_list(self, tile_ids: Tuple[int, ...], B: int, use_fast: bool):
+        key = ("crop", tile_ids, B, use_fast)
         if key not in self._wl:
-            wl, offs, total = self.plan.crop_worklist(tile_ids, B)
+            wl, offs, total = self.plan.crop_worklist(tile_ids, B, use_fast)
             self._wl[key] = (wl, offs, total) + self._upload(wl)
         return self._wl[key]
 
-    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool):
-        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8)
+    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool):
+        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast)
         if key not in self._wl:
-            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4)
+            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast)
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
@@ -163,7 +163,7 @@ class Canvas:
         """-> (flat fp32 buffer, element offsets per tile).  Tile i is
         buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
         tile_ids = tuple(int(t) for t in tile_ids)
-        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B)
+        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, bool(self.flags & nat.FLAG_FAST))
         if out is None:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
@@ -187,7 +187,7 @@ class Canvas:
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8)
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST))
         if items.shape[0] == 0:
             return
         p = self.plan

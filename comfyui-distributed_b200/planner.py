@@ -342,32 +342,50 @@ class Plan:
         ends = np.minimum(starts + block, n_out) - 1
         return int((sp[ends, 1] - sp[starts, 0]).max())
 
-    def crop_worklist(self, tile_ids: Sequence[int], B: int) -> Tuple[WorkList, np.ndarray, int]:
+    def block_shape(self, use_fast: bool) -> Tuple[int, int]:
+        return (nat.FAST_BLOCK_W, nat.FAST_BLOCK_H) if use_fast else (nat.BLOCK_W, nat.BLOCK_H)
+
+    def _crop_block_rows(self, t: Tile, use_fast: bool) -> int:
+        """Output rows per crop block.  The fast H pass maps (4-row group, channel) to lanes:
+        keep the staged input rows <= 40 so that 10 groups x 3 channels fill one warp."""
+        if not use_fast:
+            return nat.BLOCK_H
+        for bh in range(nat.FAST_BLOCK_H, 7, -1):
+            if self._span_max(t.eh, t.ph, bh, True) <= 40:
+                return bh
+        return 8
+
+    def crop_worklist(self, tile_ids: Sequence[int], B: int, use_fast: Optional[bool] = None) -> Tuple[WorkList, np.ndarray, int]:
+        use_fast = self.fast if use_fast is None else (use_fast and self.fast)
         offs, total = self.slot_offsets(tile_ids, B)
         rows = []
         pw_max = ph_max = 1
         nbytes = 0
+        bw, _ = self.block_shape(use_fast)
         for i, tid in enumerate(tile_ids):
             t = self.tiles[tid]
-            ox = np.arange(0, t.pw, nat.BLOCK_W, dtype=np.int64)
-            oy = np.arange(0, t.ph, nat.BLOCK_H, dtype=np.int64)
+            bh = self._crop_block_rows(t, use_fast)
+            ox = np.arange(0, t.pw, bw, dtype=np.int64)
+            oy = np.arange(0, t.ph, bh, dtype=np.int64)
             gx, gy = np.meshgrid(ox, oy)
             n = gx.size
             it = np.zeros((n, nat.CROP_ITEM_WORDS), dtype=np.int64)
             it[:, 0], it[:, 1], it[:, 2] = tid, gx.ravel(), gy.ravel()
-            it[:, 3], it[:, 4] = offs[i] & 0xFFFFFFFF, offs[i] >> 32
+            it[:, 3], it[:, 4], it[:, 5] = offs[i] & 0xFFFFFFFF, offs[i] >> 32, bh
             rows.append(it)
-            pw_max = max(pw_max, self._span_max(t.ew, t.pw, nat.BLOCK_W, True))
-            ph_max = max(ph_max, self._span_max(t.eh, t.ph, nat.BLOCK_H, True))
+            pw_max = max(pw_max, self._span_max(t.ew, t.pw, bw, True))
+            ph_max = max(ph_max, self._span_max(t.eh, t.ph, nat.FAST_BLOCK_H if use_fast else bh, True))
             nbytes += t.ew * t.eh * 3 + t.pw * t.ph * 3 * 4      # u8 window read + fp32 tile write
         items = np.concatenate(rows, 0) if rows else np.zeros((0, nat.CROP_ITEM_WORDS), dtype=np.int64)
         items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes), offs, total
 
-    def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4) -> WorkList:
+    def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
+                       use_fast: Optional[bool] = None) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
         given order (the order of `tile_ids` IS the blend order)."""
-        bw, bh = nat.BLOCK_W, nat.BLOCK_H
+        use_fast = self.fast if use_fast is None else (use_fast and self.fast)
+        bw, bh = self.block_shape(use_fast)
         nbx = (self.W + bw - 1) // bw
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1

@@ -82,9 +82,9 @@ typedef enum usdu_status {
 #define USDU_FAST_GROUP 8    /* consecutive outputs one thread computes from one register window */
 #define USDU_FAST_WINDOW 16  /* inputs held in that window */
 
-/* Crop work item: one BHxBW block of one tile's processing-size output. */
+/* Crop work item: one block of one tile's processing-size output. */
 #define USDU_CROP_ITEM_WORDS 6
-/*   [0]=tile id [1]=ox0 [2]=oy0 [3]=out offset lo [4]=out offset hi [5]=0
+/*   [0]=tile id [1]=ox0 [2]=oy0 [3]=out offset lo [4]=out offset hi [5]=block rows (fast path; <= 32)
  *   out offset: element offset of this tile's [B][PH][PW][3] block in `out`. */
 
 /* Blend work item: one canvas block and the ordered list of tiles composited into it. */
@@ -105,6 +105,9 @@ typedef enum usdu_status {
 /* canvas block edge used by the blend / crop kernels (pixels) */
 #define USDU_BLOCK_W 64
 #define USDU_BLOCK_H 32
+/* ... and by the fast kernels (USDU_FLAG_FAST): work items must be built with these */
+#define USDU_FAST_BLOCK_W 128
+#define USDU_FAST_BLOCK_H 32
 
 /* ---- library ------------------------------------------------------------------------ */
 int usdu_abi_version(void);

@@ -146,8 +146,10 @@ def test_mask_classes_and_worklists():
     ids = list(range(135))
     wl, offs, total = p.crop_worklist(ids, 1)
     assert total == 135 * 544 * 544 * 3
-    assert wl.items.shape == (135 * 9 * 17, nat.CROP_ITEM_WORDS)
-    bl = p.blend_worklist(ids, offs)
+    assert p.fast and wl.items.shape == (135 * 5 * 17, nat.CROP_ITEM_WORDS)        # 128 x 32 fast blocks
+    wg, _, _ = p.crop_worklist(ids, 1, use_fast=False)
+    assert wg.items.shape == (135 * 9 * 17, nat.CROP_ITEM_WORDS)                    # 64 x 32 generic blocks
+    bl = p.blend_worklist(ids, offs, use_fast=False)
     cov = bl.cover.reshape(-1, nat.COVER_WORDS)
     for it in bl.items[::997]:                            # cover lists are ascending in tile id
         c = cov[it[2]: it[2] + it[3], 0]
