@@ -123,7 +123,7 @@ struct CropEpilogue {
     }
 };
 
-__global__ void __launch_bounds__(kT, 4)
+__global__ void __launch_bounds__(kT, 2)
 crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
                  const int32_t* __restrict__ tabs, const int32_t* __restrict__ items, float* __restrict__ out,
                  int patch_w, int patch_h) {
@@ -168,7 +168,7 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch
     epi.oh = min(bh, ph - oy0);
     epi.ow3 = min(FBW, pw - ox0) * 3;
     epi.lut = lut;
-    vpass(mid, J, epi);
+    vpass(mid, J, epi, epi.oh);
 }
 
 // ======================================================================================
@@ -218,7 +218,7 @@ struct BlendFeather {
 };
 
 template <bool kSrcU8>
-__global__ void __launch_bounds__(kT, 4)
+__global__ void __launch_bounds__(kT, 2)
 blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
                   const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
                   const int32_t* __restrict__ items, const int32_t* __restrict__ cover,
@@ -277,7 +277,7 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, con
             BlendOpaque epi;
             epi.dst = cblk;
             epi.pitch = pitch;
-            vpass(mid, J, epi);
+            vpass(mid, J, epi, FBH);
         } else {
             BlendFeather epi;
             epi.dst = cblk;
@@ -285,7 +285,7 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, con
             epi.mpitch = T[USDU_T_MASK_PITCH];
             epi.mask = mask_pool + (int64_t)(uint32_t)T[USDU_T_MASK_OFF] + (int64_t)oy_base * epi.mpitch + ox_base;
             epi.cx0 = X0 - bx0; epi.cx1 = X1 - bx0; epi.cy0 = Y0 - by0; epi.cy1 = Y1 - by0;
-            vpass(mid, J, epi);
+            vpass(mid, J, epi, epi.cy1);
         }
     }
 }
