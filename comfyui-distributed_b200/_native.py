@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -33,6 +33,11 @@ BLOCK_W = 64
 BLOCK_H = 32
 FAST_BLOCK_W = 128
 FAST_BLOCK_H = 32
+FAST_TAPS = 7
+JOB_WORDS = 32
+(J_SRC_A, J_SRC_B, J_LEAD, J_COLS, J_ROWS, J_IX0, J_IY0, J_ROWS_H, J_OX_BASE, J_N_OUT_H, J_ROWS_V, J_OY_BASE, J_N_OUT_V,
+ J_DST_X, J_DST_Y, J_OFF_LO, J_OFF_HI, J_ROWS_OUT, J_COLS_OUT, J_CX0, J_CX1, J_CY0, J_CY1, J_FLAGS, J_MPITCH, J_PITCH,
+ J_FRAME_LO, J_FRAME_HI, J_NEXT) = range(29)
 
 
 class NativeError(RuntimeError):

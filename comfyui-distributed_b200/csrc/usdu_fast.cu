@@ -5,25 +5,6 @@
 namespace usdu {
 namespace fast {
 
-// ---- table access -------------------------------------------------------------------------
-struct Axis {
-    const int32_t* rows;  // packed rows
-    int n_in, n_out;
-};
-
-__device__ __forceinline__ Axis axis_of(const int32_t* tabs, int tab) {
-    const int32_t* t = tabs + tab;
-    Axis a;
-    a.n_in = t[0];
-    a.n_out = t[1];
-    a.rows = t + t[4];
-    return a;
-}
-
-__device__ __forceinline__ int first_of(const Axis& a, int out_idx) {
-    return __ldg(a.rows + (size_t)clampi(out_idx, 0, a.n_out - 1) * USDU_PACKED_ROW);
-}
-
 // Transpose 4 registers (rows) x 4 bytes (columns) -> 4 words, word j = byte j of rows 0..3.
 __device__ __forceinline__ void transpose4x4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t (&o)[4]) {
     const uint32_t a = __byte_perm(r0, r1, 0x5140), b = __byte_perm(r0, r1, 0x7362);   // (r0.b0 r1.b0 r0.b1 r1.b1), (.. b2 b3)
@@ -106,16 +87,37 @@ __device__ __forceinline__ void stage_f32(uint32_t* __restrict__ in, int xw, con
     }
 }
 
+// Load the job record of this CTA (thread 0..7 -> one int4 each) and the V-axis rows.
+__device__ __forceinline__ void load_job(int32_t* job_sm, const int32_t* __restrict__ jobs, int idx) {
+    if (threadIdx.x < USDU_JOB_WORDS / 4)
+        reinterpret_cast<int4*>(job_sm)[threadIdx.x] =
+            __ldg(reinterpret_cast<const int4*>(jobs + (size_t)idx * USDU_JOB_WORDS) + threadIdx.x);
+}
+
+__device__ __forceinline__ void stage_rows_v(int32_t* rows_sm, const int32_t* __restrict__ tabs, const JobView& J) {
+    if (threadIdx.x < FBH * 2) {
+        const int o = clampi(J[USDU_J_OY_BASE] + (threadIdx.x >> 1), 0, J[USDU_J_N_OUT_V] - 1);
+        reinterpret_cast<int4*>(rows_sm)[threadIdx.x] =
+            __ldg(reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_V] + (size_t)o * USDU_PACKED_ROW) + (threadIdx.x & 1));
+    }
+}
+
+__device__ __forceinline__ PackedRow load_row_h(const int32_t* __restrict__ tabs, const JobView& J) {
+    const int o = clampi(J[USDU_J_OX_BASE] + (int)(threadIdx.x % FBW), 0, J[USDU_J_N_OUT_H] - 1);
+    const int4* p = reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_H] + (size_t)o * USDU_PACKED_ROW);
+    return unpack_row(__ldg(p), __ldg(p + 1));
+}
+
 // ======================================================================================
 // crop + resize
 // ======================================================================================
 struct CropEpilogue {
     float* dst;          // &out[tile][b][oy0][ox0][0]
     int64_t row_pitch;   // floats per output row
-    int oh, ow3;
+    int ow3;
     const float* lut;
     __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
-        if (r < oh && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
+        if (4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
             float4 o;
             o.x = lut[s[0]]; o.y = lut[s[1]]; o.z = lut[s[2]]; o.w = lut[s[3]];
             __stcs(reinterpret_cast<float4*>(dst + (int64_t)r * row_pitch + 4 * strip), o);
@@ -123,52 +125,35 @@ struct CropEpilogue {
     }
 };
 
-__global__ void __launch_bounds__(kT, 2)
-crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
-                 const int32_t* __restrict__ tabs, const int32_t* __restrict__ items, float* __restrict__ out,
-                 int patch_w, int patch_h) {
+__global__ void __launch_bounds__(kT, 4)
+crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
+                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int patch_h) {
     extern __shared__ __align__(16) uint8_t smem[];
-    int32_t* rows_h = reinterpret_cast<int32_t*>(smem);
-    int32_t* rows_v = rows_h + FBW * USDU_PACKED_ROW;
-    float* lut = reinterpret_cast<float*>(smem + kRowsBytes);
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kRowsBytes + 1024);
-    uint8_t* mid = smem + kRowsBytes + 1024 + in_bytes(patch_w, patch_h);
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem);
+    int32_t* rows_v = job_sm + USDU_JOB_WORDS;
+    float* lut = reinterpret_cast<float*>(smem + kHeadBytes);
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kHeadBytes + 1024);
+    uint8_t* mid = smem + kHeadBytes + 1024 + in_bytes(patch_w, patch_h);
+    load_job(job_sm, jobs, blockIdx.x);
     for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8(i);
-
-    const int32_t* it = items + (int64_t)blockIdx.x * USDU_CROP_ITEM_WORDS;
-    const int32_t* T = tiles + (int64_t)it[0] * USDU_TILE_WORDS;
-    const int b = blockIdx.y;
-    const int ox0 = it[1], oy0 = it[2], bh = it[5];
-    const int64_t out_off = (int64_t)(uint32_t)it[3] | ((int64_t)it[4] << 32);
-    const int x1 = T[USDU_T_X1], y1 = T[USDU_T_Y1], pw = T[USDU_T_PW], ph = T[USDU_T_PH];
-    const Axis ah = axis_of(tabs, T[USDU_T_TAB_CROP_H]), av = axis_of(tabs, T[USDU_T_TAB_CROP_V]);
-    stage_rows(rows_h, ah.rows, ah.n_out, ox0, FBW);
-    stage_rows(rows_v, av.rows, av.n_out, oy0, FBH);
-
-    Job J;
-    J.rows_h = rows_h; J.rows_v = rows_v;
-    J.ix0 = first_of(ah, ox0);
-    J.iy0 = first_of(av, oy0);
-    const int ix1 = min(first_of(ah, ox0 + FBW - 1) + TAPS, ah.n_in);
-    const int iy1 = min(first_of(av, oy0 + bh - 1) + TAPS, av.n_in);
-    J.rows_in = iy1 - J.iy0;
-    J.xw = plane_words(patch_w);
-
-    // canvas bytes of the patch: row (y1 + iy0 + r), from pixel x1 + ix0; align down to 4 pixels
-    const int px_abs = x1 + J.ix0;
-    const int lead = px_abs & 3;
-    const uint8_t* src = canvas + ((int64_t)b * H + (y1 + J.iy0)) * pitch + (int64_t)(px_abs - lead) * 3;
-    stage_u8(in, J.xw, src, pitch, J.rows_in, J.rows_in, ix1 - J.ix0, lead);
     __syncthreads();
-    hpass(in, mid, J);
+    const JobView J{job_sm};
+    const int b = blockIdx.y;
+    const int xw = plane_words(patch_w);
+    const PackedRow rh = load_row_h(tabs, J);
+    stage_rows_v(rows_v, tabs, J);
+    const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
+    stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
+    __syncthreads();
+    hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
     __syncthreads();
     CropEpilogue epi;
-    epi.dst = out + out_off + ((int64_t)b * ph + oy0) * pw * 3 + (int64_t)ox0 * 3;
-    epi.row_pitch = (int64_t)pw * 3;
-    epi.oh = min(bh, ph - oy0);
-    epi.ow3 = min(FBW, pw - ox0) * 3;
+    epi.row_pitch = J[USDU_J_PITCH];
+    epi.dst = out + J.i64(USDU_J_OFF_LO) + (int64_t)b * J.i64(USDU_J_FRAME_LO) + (int64_t)J[USDU_J_DST_Y] * epi.row_pitch +
+              (int64_t)J[USDU_J_DST_X] * 3;
+    epi.ow3 = J[USDU_J_COLS_OUT] * 3;
     epi.lut = lut;
-    vpass(mid, J, epi, epi.oh);
+    vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, J[USDU_J_ROWS_OUT]);
 }
 
 // ======================================================================================
@@ -189,9 +174,8 @@ struct BlendFeather {
     int64_t pitch;
     const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
     int mpitch;
-    int cx0, cx1, cy0, cy1;   // sub-rect in block pixel coordinates
+    int cx0, cx1;          // sub-rect columns in block pixel coordinates (rows are bounded by the caller)
     __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
-        if (r < cy0 || r >= cy1) return;
         const int col = 4 * strip;
         const int pa = col / 3, pb = (col + 3) / 3;          // the 4 bytes touch pixels pa and pb (pb = pa or pa+1)
         const bool ina = pa >= cx0 && pa < cx1, inb = pb >= cx0 && pb < cx1;
@@ -218,80 +202,56 @@ struct BlendFeather {
 };
 
 template <bool kSrcU8>
-__global__ void __launch_bounds__(kT, 2)
-blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
-                  const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
-                  const int32_t* __restrict__ items, const int32_t* __restrict__ cover,
+__global__ void __launch_bounds__(kT, 4)
+blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
+                  const uint8_t* __restrict__ mask_pool, const int32_t* __restrict__ jobs,
                   const void* __restrict__ src_v, int patch_w, int patch_h) {
     extern __shared__ __align__(16) uint8_t smem[];
-    int32_t* rows_h = reinterpret_cast<int32_t*>(smem);
-    int32_t* rows_v = rows_h + FBW * USDU_PACKED_ROW;
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kRowsBytes);
-    uint8_t* mid = smem + kRowsBytes + in_bytes(patch_w, patch_h);
-
-    const int32_t* it = items + (int64_t)blockIdx.x * USDU_BLEND_ITEM_WORDS;
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem);
+    int32_t* rows_v = job_sm + USDU_JOB_WORDS;
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kHeadBytes);
+    uint8_t* mid = smem + kHeadBytes + in_bytes(patch_w, patch_h);
     const int b = blockIdx.y;
-    const int bx0 = it[0], by0 = it[1];
-    const int bw = min(FBW, W - bx0), bh = min(FBH, H - by0);
-    uint8_t* cblk = canvas + ((int64_t)b * H + by0) * pitch + (int64_t)bx0 * 3;
-    const int c0 = it[2], cn = it[3];
-    for (int e = 0; e < cn; ++e) {
-        const int32_t* C = cover + (int64_t)(c0 + e) * USDU_COVER_WORDS;
-        const int32_t* T = tiles + (int64_t)C[0] * USDU_TILE_WORDS;
-        const int64_t src_off = (int64_t)(uint32_t)C[1] | ((int64_t)C[2] << 32);
-        const int x1 = T[USDU_T_X1], y1 = T[USDU_T_Y1];
-        const int pw = T[USDU_T_PW], ph = T[USDU_T_PH];
-        // block  ∩  support of the feather template (alpha == 0 outside), canvas coordinates
-        const int X0 = max(bx0, x1 + T[USDU_T_SUP_X0]), X1 = min(bx0 + bw, x1 + T[USDU_T_SUP_X1]);
-        const int Y0 = max(by0, y1 + T[USDU_T_SUP_Y0]), Y1 = min(by0 + bh, y1 + T[USDU_T_SUP_Y1]);
-        if (X1 <= X0 || Y1 <= Y0) continue;   // uniform
-        const Axis ah = axis_of(tabs, T[USDU_T_TAB_BLEND_H]), av = axis_of(tabs, T[USDU_T_TAB_BLEND_V]);
-        const int ox_base = bx0 - x1, oy_base = by0 - y1;
-        __syncthreads();   // the previous tile's passes are done with rows / in / mid
-        stage_rows(rows_h, ah.rows, ah.n_out, ox_base, FBW);
-        stage_rows(rows_v, av.rows, av.n_out, oy_base, FBH);
-        Job J;
-        J.rows_h = rows_h; J.rows_v = rows_v;
-        J.ix0 = first_of(ah, ox_base);
-        J.iy0 = first_of(av, oy_base);
-        const int ix1 = min(first_of(ah, ox_base + FBW - 1) + TAPS, ah.n_in);
-        const int iy1 = min(first_of(av, oy_base + FBH - 1) + TAPS, av.n_in);
-        J.rows_in = iy1 - J.iy0;
-        J.xw = plane_words(patch_w);
-        const int lead = J.ix0 & 3;
-        const int64_t frame = (int64_t)ph * pw * 3;
-        const int64_t first = src_off + b * frame + ((int64_t)J.iy0 * pw + (J.ix0 - lead)) * 3;
+    const int xw = plane_words(patch_w);
+    const JobView J{job_sm};
+    int idx = blockIdx.x;
+    while (idx >= 0) {
+        __syncthreads();                       // the previous tile's passes are done with job / rows / in / mid
+        load_job(job_sm, jobs, idx);
+        __syncthreads();
+        const PackedRow rh = load_row_h(tabs, J);
+        stage_rows_v(rows_v, tabs, J);
+        const int64_t first = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
         if (kSrcU8)
-            stage_u8(in, J.xw, static_cast<const uint8_t*>(src_v) + first, (int64_t)pw * 3, J.rows_in, J.rows_in,
-                     ix1 - J.ix0, lead);
+            stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+                     J[USDU_J_COLS], J[USDU_J_LEAD]);
         else
-            stage_f32(in, J.xw, static_cast<const float*>(src_v) + first, (int64_t)pw * 3, J.rows_in, J.rows_in,
-                      ix1 - J.ix0, lead);
+            stage_f32(in, xw, static_cast<const float*>(src_v) + first, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+                      J[USDU_J_COLS], J[USDU_J_LEAD]);
         __syncthreads();
-        hpass(in, mid, J);
+        hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
         __syncthreads();
-        // whole block inside the opaque core of this tile?
-        const bool opaque = bw == FBW && bh == FBH && bx0 >= x1 + T[USDU_T_FULL_X0] && bx0 + FBW <= x1 + T[USDU_T_FULL_X1] &&
-                            by0 >= y1 + T[USDU_T_FULL_Y0] && by0 + FBH <= y1 + T[USDU_T_FULL_Y1];
-        if (opaque) {
+        uint8_t* cblk = canvas + ((int64_t)b * H + J[USDU_J_DST_Y]) * pitch + (int64_t)J[USDU_J_DST_X] * 3;
+        if (J[USDU_J_FLAGS] & 1) {
             BlendOpaque epi;
             epi.dst = cblk;
             epi.pitch = pitch;
-            vpass(mid, J, epi, FBH);
+            vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, FBH);
         } else {
             BlendFeather epi;
             epi.dst = cblk;
             epi.pitch = pitch;
-            epi.mpitch = T[USDU_T_MASK_PITCH];
-            epi.mask = mask_pool + (int64_t)(uint32_t)T[USDU_T_MASK_OFF] + (int64_t)oy_base * epi.mpitch + ox_base;
-            epi.cx0 = X0 - bx0; epi.cx1 = X1 - bx0; epi.cy0 = Y0 - by0; epi.cy1 = Y1 - by0;
-            vpass(mid, J, epi, epi.cy1);
+            epi.mpitch = J[USDU_J_MPITCH];
+            epi.mask = mask_pool + J.i64(USDU_J_OFF_LO);
+            epi.cx0 = J[USDU_J_CX0]; epi.cx1 = J[USDU_J_CX1];
+            vpass(mid, rows_v, J[USDU_J_IY0], epi, J[USDU_J_CY0], J[USDU_J_CY1]);
         }
+        idx = J[USDU_J_NEXT];
     }
 }
 
-static size_t crop_smem(int patch_w, int patch_h) { return kRowsBytes + 1024 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
-static size_t blend_smem(int patch_w, int patch_h) { return kRowsBytes + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t crop_smem(int patch_w, int patch_h) { return kHeadBytes + 1024 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t blend_smem(int patch_w, int patch_h) { return kHeadBytes + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
 
 static int optin(const void* fn, size_t bytes) {
     if (bytes > 227 * 1024) {
@@ -307,7 +267,7 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
     const size_t smem = crop_smem(patch_w, patch_h);
     int s = optin((const void*)crop_fast_kernel, smem);
     if (s != USDU_OK) return s;
-    crop_fast_kernel<<<dim3(n_items, B), kT, smem, st>>>(canvas, H, W, pitch, tiles, tabs, items, out, patch_w, patch_h);
+    crop_fast_kernel<<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
@@ -320,11 +280,9 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (src_is_u8)
-        blend_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, W, pitch, tiles, tabs, mask_pool, items,
-                                                                     cover, src, patch_w, patch_h);
+        blend_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, mask_pool, items, src, patch_w, patch_h);
     else
-        blend_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, W, pitch, tiles, tabs, mask_pool, items,
-                                                                      cover, src, patch_w, patch_h);
+        blend_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, mask_pool, items, src, patch_w, patch_h);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

@@ -6,10 +6,9 @@
 // The naive form -- one shared-memory byte load + one IMAD per tap -- needs ~300 thread
 // instructions per output byte.  Here one 32-bit shared-memory load brings the tap's byte
 // of FOUR independent lines (rows in the H pass, byte columns in the V pass), so a tap costs
-// 1/4 LDS + PRMT + IMAD per byte, registers stay ~40 (12 CTAs of 128 threads per SM) and
-// no dynamic register indexing is needed.  (A register-window variant with a warp-uniform
-// switch was measured first: 63 instr/byte at 16 warps/SM -- profiles/r01c_*; this form is
-// simpler and faster.)
+// 1/4 LDS + PRMT + IMAD per byte, registers stay <= 64 and no dynamic register indexing is
+// needed.  (A register-window variant with a warp-uniform switch was measured first: 63
+// instr/byte at 16 warps/SM -- profiles/r01c_*; this form is simpler and faster.)
 //
 //   H pass  thread = output pixel column (coefficients in registers), loop over (group of 4
 //           rows, channel).  Input is staged PLANAR and ROW-PACKED: word(g, c, x) = bytes of
@@ -26,12 +25,10 @@
 namespace usdu {
 namespace fast {
 
-constexpr int kT = 512;                    // threads per CTA: 4 sub-groups of FBW threads
+constexpr int kT = 256;                    // threads per CTA: 2 sub-groups of FBW threads
 constexpr int FBW = USDU_FAST_BLOCK_W;     // 128-pixel wide blocks
 constexpr int FBH = USDU_FAST_BLOCK_H;     // up to 32 rows
 constexpr int TAPS = USDU_FAST_TAPS;       // 7
-constexpr int GROUP = USDU_FAST_GROUP;     // 8 outputs per window
-constexpr int WIN = USDU_FAST_WINDOW;      // 16 inputs per window
 constexpr int R = 4;                       // independent lines (rows / byte columns) per thread
 constexpr int MID_PITCH = FBW * 3 + 4;     // 388 bytes: 4 consecutive rows land 4 banks apart
 
@@ -40,33 +37,14 @@ struct PackedRow {  // one output of an axis: first input index + 7 coefficients
     int k[TAPS];
 };
 
-__device__ __forceinline__ PackedRow load_row(const int32_t* rows, int idx) {
-    const int4* p = reinterpret_cast<const int4*>(rows + (size_t)idx * USDU_PACKED_ROW);
-    const int4 a = p[0], b = p[1];
+__device__ __forceinline__ PackedRow unpack_row(const int4 a, const int4 b) {
     PackedRow r;
     r.first = a.x; r.k[0] = a.y; r.k[1] = a.z; r.k[2] = a.w;
     r.k[3] = b.x; r.k[4] = b.y; r.k[5] = b.z; r.k[6] = b.w;
     return r;
 }
 
-// Geometry of one (block, tile) resampling job, all warp-uniform.
-struct Job {
-    const int32_t* rows_h;  // shared memory: packed rows of block pixel columns 0..FBW-1 (already clamped)
-    const int32_t* rows_v;  // shared memory: packed rows of block rows 0..FBH-1
-    int ix0, iy0;           // first input column / row held in shared memory
-    int rows_in;            // staged input rows
-    int xw;                 // words per (g, c) plane row of `in`
-};
-
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-// Copy the packed rows of outputs base .. base+count-1 (clamped to the axis) into shared memory.
-__device__ __forceinline__ void stage_rows(int32_t* dst, const int32_t* rows, int n_out, int base, int count) {
-    for (int i = threadIdx.x; i < count * 2; i += kT) {
-        const int o = clampi(base + (i >> 1), 0, n_out - 1);
-        reinterpret_cast<int4*>(dst)[i] = __ldg(reinterpret_cast<const int4*>(rows + (size_t)o * USDU_PACKED_ROW) + (i & 1));
-    }
-}
 
 // clip8(acc >> 22) in two instructions (SHF + VIMNMX.RELU)
 __device__ __forceinline__ uint32_t finish(int acc) {
@@ -84,18 +62,26 @@ __device__ __forceinline__ void dot4(const uint32_t (&w)[TAPS], const PackedRow&
     }
 }
 
+// The job record, staged in shared memory (warp-uniform reads).
+struct JobView {
+    const int32_t* j;
+    __device__ __forceinline__ int operator[](int i) const { return j[i]; }
+    __device__ __forceinline__ int64_t i64(int lo) const {
+        return (int64_t)(uint32_t)j[lo] | ((int64_t)j[lo + 1] << 32);
+    }
+};
+
 // ---- H pass: in (planar, row packed) -> mid[row][block px * 3 + c] ----------------------
-// thread = one block pixel column (its 7 coefficients stay in registers), loop over the
-// (4-row group, channel) planes; one LDS.32 per tap feeds 4 rows.
-__device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const Job& J) {
+// `row` = this thread's pixel column coefficients (loaded from global before staging).
+__device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const PackedRow& row,
+                                      int ix0, int rows_in, int xw) {
     const int px = threadIdx.x % FBW, sub = threadIdx.x / FBW;
-    const PackedRow row = load_row(J.rows_h, px);
-    const uint32_t* w0 = in + (row.first - J.ix0);
-    const int units = ((J.rows_in + 3) >> 2) * 3;
+    const uint32_t* w0 = in + (row.first - ix0);
+    const int units = ((rows_in + 3) >> 2) * 3;
     uint8_t* o = mid + px * 3;
 #pragma unroll 2
     for (int u = sub; u < units; u += kT / FBW) {
-        const uint32_t* wp = w0 + (size_t)u * J.xw;
+        const uint32_t* wp = w0 + (size_t)u * xw;
         uint32_t w[TAPS];
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) w[t] = wp[t];
@@ -109,17 +95,20 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* 
 }
 
 // ---- V pass: mid -> S values, handed to an epilogue -------------------------------------
-// item = (block row, 4-byte column strip); one LDS.32 per tap feeds 4 byte columns.
+// rows_v: shared-memory copy of the packed rows of block rows 0..FBH-1.
 // Epilogue::row(int block_row, int strip, const uint32_t (&s)[4]).
 template <class Epilogue>
-__device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const Job& J, Epilogue& epi, int rows_out) {
+__device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int32_t* rows_v, int iy0, Epilogue& epi,
+                                      int row_begin, int row_end) {
     constexpr int STRIPS = FBW * 3 / 4;             // 96
-    const int total = rows_out * STRIPS;
+    const int total = (row_end - row_begin) * STRIPS;
 #pragma unroll 2
     for (int it = threadIdx.x; it < total; it += kT) {
-        const int r = it / STRIPS, strip = it - r * STRIPS;
-        const PackedRow row = load_row(J.rows_v, r);
-        const uint8_t* m = mid + (size_t)(row.first - J.iy0) * MID_PITCH + 4 * strip;
+        const int rr = it / STRIPS, strip = it - rr * STRIPS;
+        const int r = row_begin + rr;
+        const int4* rp = reinterpret_cast<const int4*>(rows_v + r * USDU_PACKED_ROW);
+        const PackedRow row = unpack_row(rp[0], rp[1]);
+        const uint8_t* m = mid + (size_t)(row.first - iy0) * MID_PITCH + 4 * strip;
         uint32_t w[TAPS];
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) w[t] = *reinterpret_cast<const uint32_t*>(m + (size_t)t * MID_PITCH);
@@ -141,7 +130,7 @@ __host__ __device__ inline size_t in_bytes(int patch_w, int patch_h) {
 __host__ __device__ inline size_t mid_bytes(int patch_h) {
     return ((size_t)((patch_h + 3) / 4 * 4 + 1) * MID_PITCH + 15) / 16 * 16;
 }
-constexpr size_t kRowsBytes = (size_t)(FBW + FBH) * USDU_PACKED_ROW * 4;   // staged coefficient rows
+constexpr size_t kHeadBytes = USDU_JOB_WORDS * 4 + (size_t)FBH * USDU_PACKED_ROW * 4;   // job record + rows_v
 
 }  // namespace fast
 }  // namespace usdu

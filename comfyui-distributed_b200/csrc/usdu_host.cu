@@ -135,7 +135,7 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
     }
     table[3] = tmax;
     table[5] = span;
-    const bool fast = tmax <= USDU_FAST_TAPS && span <= USDU_FAST_WINDOW;
+    const bool fast = tmax <= USDU_FAST_TAPS;
     table[4] = fast ? (int32_t)(packed - table) : 0;
     for (int xx = 0; xx < out_size; xx++) {
         int32_t* r = packed + (int64_t)xx * USDU_PACKED_ROW;

@@ -577,7 +577,7 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, con
                     const int32_t* tabs_dev, const uint8_t* mask_pool_dev, const int32_t* items_dev,
                     int n_items, const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
                     int src_is_u8, int flags, void* stream) {
-    USDU_REQUIRE(canvas_dev && tiles_dev && mask_pool_dev && items_dev && cover_dev && src_dev,
+    USDU_REQUIRE(canvas_dev && tiles_dev && mask_pool_dev && items_dev && src_dev && (cover_dev || (flags & USDU_FLAG_FAST)),
                  "usdu_tile_blend: null pointer");
     USDU_REQUIRE(B > 0 && H > 0 && W > 0 && n_items >= 0, "usdu_tile_blend: bad shape");
     USDU_REQUIRE(B <= 65535, "usdu_tile_blend: batch %d exceeds grid.y limit", B);

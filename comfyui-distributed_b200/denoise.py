@@ -21,8 +21,11 @@ import torch
 
 
 class T0Denoiser:
+    cuda_graph_safe = True    # pure elementwise device work on fixed shapes
+
     def __init__(self, seed: int, denoise: float):
         self.seed = int(seed)
+        self.graph_key = ("t0", int(seed), float(np.float32(denoise)))
         # every step individually rounded in fp32 so CPU (oracle) and GPU agree bit-for-bit
         self.d = float(np.float32(denoise))
         self.omd = float(np.float32(1.0) - np.float32(denoise))

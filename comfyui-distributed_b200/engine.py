@@ -34,19 +34,28 @@ class KernelProfile:
     Usage: prof = KernelProfile(); engine.PROFILE = prof; ...; prof.summary()."""
 
     def __init__(self):
-        self.rec = []   # (name, ev0, ev1, algorithmic bytes)
+        self.rec = []          # (name, ev0, ev1, algorithmic bytes) of eager launches since begin_step()
+        self.graph_rec = []    # the same for launches captured into a CUDA graph (re-recorded on every replay)
+        self.capturing = False
+
+    def begin_step(self):
+        """Forget the eager records of earlier steps: summary() then describes ONE step."""
+        self.rec = []
 
     def launch(self, name: str, nbytes: int, fn):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # external=True: inside a CUDA-graph capture these become event-record NODES, so the
+        # timestamps are taken on the device between back-to-back kernels (no host gaps)
+        e0 = torch.cuda.Event(enable_timing=True, external=True)
+        e1 = torch.cuda.Event(enable_timing=True, external=True)
         e0.record()
         fn()
         e1.record()
-        self.rec.append((name, e0, e1, nbytes))
+        (self.graph_rec if self.capturing else self.rec).append((name, e0, e1, nbytes))
 
     def summary(self) -> dict:
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, nb in self.rec:
+        for name, e0, e1, nb in self.rec + self.graph_rec:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -59,6 +68,7 @@ class KernelProfile:
 
 PROFILE: Optional[KernelProfile] = None
 FORCE_GENERIC = False     # tests: run the generic (any-scale) kernels even when the fast ones apply
+USE_CUDA_GRAPHS = True    # capture the wave loop when the sampler is cuda_graph_safe
 
 
 def _launch(name: str, nbytes: int, fn):
@@ -192,10 +202,12 @@ class Canvas:
             return
         p = self.plan
         src = src.contiguous()
+        n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
+        cover_ptr = cover.data_ptr() if cover is not None else 0
         _launch("blend", wl.algo_bytes * self.B,
                 lambda: nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
                                        self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(),
-                                       items.shape[0], cover.data_ptr(), wl.patch_w, wl.patch_h, src.data_ptr(),
+                                       n_grid, cover_ptr, wl.patch_w, wl.patch_h, src.data_ptr(),
                                        src_u8, self.flags, _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
@@ -267,17 +279,77 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     return shipped
 
 
+class GraphedWaves:
+    """The wave loop of a progressive job (crop -> sampler -> blend, x waves) captured once
+    into a CUDA graph on a static canvas: one graph launch replaces ~5 kernel launches per
+    wave, which removes the host enqueue gaps that dominate when the sampler is cheap.
+    Only for samplers that declare `cuda_graph_safe` (pure device work, fixed shapes)."""
+
+    _cache: Dict[tuple, "GraphedWaves"] = {}
+
+    def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile]):
+        global PROFILE
+        self.canvas = Canvas(dp, B)
+        self.denoiser = denoiser
+        order = range(len(dp.plan.tiles))
+        self.canvas.buf.zero_()
+        side = torch.cuda.Stream(device=dp.device)
+        side.wait_stream(torch.cuda.current_stream(dp.device))
+        saved = PROFILE
+        PROFILE = None
+        with torch.cuda.stream(side):                 # warm-up: fills every cache (work lists, noise)
+            run_progressive(self.canvas, order, denoiser)
+        torch.cuda.current_stream(dp.device).wait_stream(side)
+        torch.cuda.synchronize(dp.device)
+        self.canvas.launches = 0
+        self.canvas.algo_bytes = 0
+        PROFILE = profile
+        self.graph = torch.cuda.CUDAGraph()
+        if profile is not None:
+            profile.capturing = True
+        try:
+            with torch.cuda.graph(self.graph):
+                run_progressive(self.canvas, order, denoiser)
+        finally:
+            PROFILE = saved
+            if profile is not None:
+                profile.capturing = False
+        self.launches_per_replay = self.canvas.launches
+        self.bytes_per_replay = self.canvas.algo_bytes
+
+    @classmethod
+    def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None) -> "GraphedWaves":
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC)
+        gw = cls._cache.get(key)
+        if gw is None or gw.canvas.dp is not dp:
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile)
+        return gw
+
+
 def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
-                   mask_blur: int, force_uniform_tiles: bool = True, stats: Optional[dict] = None) -> torch.Tensor:
+                   mask_blur: int, force_uniform_tiles: bool = True, stats: Optional[dict] = None,
+                   use_graph: Optional[bool] = None) -> torch.Tensor:
     """One-GPU job on a CUDA image [B,H,W,3] fp32 -> fp32 (values k/255), exact
     progressive semantics of process_single_gpu."""
     _require_cuda(image, "image")
     B, H, W, _ = image.shape
     plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
+    if use_graph is None:
+        use_graph = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
-        canvas = Canvas(dp, B).load(image)
-        run_progressive(canvas, range(len(plan.tiles)), denoiser)
+        if use_graph:
+            gw = GraphedWaves.get(dp, B, denoiser, PROFILE)
+            canvas = gw.canvas
+            canvas.launches, canvas.algo_bytes = gw.launches_per_replay, gw.bytes_per_replay
+            canvas.flags = nat.FLAG_FAST if (plan.fast and not FORCE_GENERIC) else 0
+            canvas.load(image)                        # Q0, eager, straight from the caller's tensor
+            gw.graph.replay()
+        else:
+            canvas = Canvas(dp, B).load(image)
+            run_progressive(canvas, range(len(plan.tiles)), denoiser)
         res = canvas.result()
     if stats is not None:
         stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches

@@ -116,6 +116,7 @@ class WorkList:
     patch_w: int
     patch_h: int
     algo_bytes: int                   # algorithmic HBM bytes of the launch per frame
+    n_launch: int = -1                # grid size when it differs from len(items) (chained fast jobs)
 
 
 @dataclass
@@ -139,6 +140,8 @@ class Plan:
     fast: bool = True                     # every table has packed rows -> register-window kernels
     _tab_off: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_span: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
+    _tab_packed: Dict[Tuple[int, int], int] = field(default_factory=dict)
+    _tab_first: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
 
     # ---- construction ---------------------------------------------------------------
     @staticmethod
@@ -166,7 +169,9 @@ class Plan:
             off = 0 if self.tabs is None else int(self.tabs.shape[0])
             self.tabs = tab if self.tabs is None else np.concatenate([self.tabs, tab])
             self._tab_off[key] = off
+            self._tab_packed[key] = off + int(tab[4])          # pool index of packed row 0 (fast kernels)
             b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
+            self._tab_first[key] = b[:, 0].astype(np.int64)
             self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], 7)], 1)   # [lo, hi) per output (>= 7 taps staged)
         return self._tab_off[key]
 
@@ -377,8 +382,49 @@ class Plan:
             ph_max = max(ph_max, self._span_max(t.eh, t.ph, nat.FAST_BLOCK_H if use_fast else bh, True))
             nbytes += t.ew * t.eh * 3 + t.pw * t.ph * 3 * 4      # u8 window read + fp32 tile write
         items = np.concatenate(rows, 0) if rows else np.zeros((0, nat.CROP_ITEM_WORDS), dtype=np.int64)
+        if use_fast and items.shape[0]:
+            items = self._crop_jobs(items)
         items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes), offs, total
+
+    def _first(self, key: Tuple[int, int], idx: np.ndarray) -> np.ndarray:
+        f = self._tab_first[key]
+        return f[np.clip(idx, 0, f.shape[0] - 1)]
+
+    def _crop_jobs(self, items: np.ndarray) -> np.ndarray:
+        """Generic crop items [tile, ox0, oy0, off_lo, off_hi, bh] -> fast job records."""
+        n = items.shape[0]
+        J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
+        tid, ox0, oy0, bh = items[:, 0], items[:, 1], items[:, 2], items[:, 5]
+        geo = np.array([[t.x1, t.y1, t.ew, t.eh, t.pw, t.ph] for t in self.tiles], dtype=np.int64)[tid]
+        x1, y1, ew, eh, pw, ph = geo.T
+        ix0 = np.zeros(n, np.int64); ix1 = np.zeros(n, np.int64); iy0 = np.zeros(n, np.int64); iy1 = np.zeros(n, np.int64)
+        rows_h = np.zeros(n, np.int64); rows_v = np.zeros(n, np.int64)
+        for key in {(int(a), int(b)) for a, b in zip(ew, pw)}:
+            m = (ew == key[0]) & (pw == key[1])
+            ix0[m] = self._first(key, ox0[m])
+            ix1[m] = np.minimum(self._first(key, ox0[m] + nat.FAST_BLOCK_W - 1) + nat.FAST_TAPS, key[0])
+            rows_h[m] = self._tab_packed[key]
+        for key in {(int(a), int(b)) for a, b in zip(eh, ph)}:
+            m = (eh == key[0]) & (ph == key[1])
+            iy0[m] = self._first(key, oy0[m])
+            iy1[m] = np.minimum(self._first(key, oy0[m] + bh[m] - 1) + nat.FAST_TAPS, key[0])
+            rows_v[m] = self._tab_packed[key]
+        px_abs = x1 + ix0
+        lead = px_abs & 3
+        J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_LEAD] = px_abs - lead, y1 + iy0, lead
+        J[:, nat.J_COLS], J[:, nat.J_ROWS], J[:, nat.J_IX0], J[:, nat.J_IY0] = ix1 - ix0, iy1 - iy0, ix0, iy0
+        J[:, nat.J_ROWS_H], J[:, nat.J_OX_BASE], J[:, nat.J_N_OUT_H] = rows_h, ox0, pw
+        J[:, nat.J_ROWS_V], J[:, nat.J_OY_BASE], J[:, nat.J_N_OUT_V] = rows_v, oy0, ph
+        J[:, nat.J_DST_X], J[:, nat.J_DST_Y] = ox0, oy0
+        J[:, nat.J_OFF_LO], J[:, nat.J_OFF_HI] = items[:, 3], items[:, 4]
+        J[:, nat.J_ROWS_OUT] = np.minimum(bh, ph - oy0)
+        J[:, nat.J_COLS_OUT] = np.minimum(nat.FAST_BLOCK_W, pw - ox0)
+        J[:, nat.J_PITCH] = pw * 3
+        frame = ph * pw * 3
+        J[:, nat.J_FRAME_LO], J[:, nat.J_FRAME_HI] = frame & 0xFFFFFFFF, frame >> 32
+        J[:, nat.J_NEXT] = -1
+        return J
 
     def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
                        use_fast: Optional[bool] = None) -> WorkList:
@@ -417,11 +463,73 @@ class Plan:
         items[:, 1] = (keys[first] // nbx) * bh
         items[:, 2] = first
         items[:, 3] = counts
+        if use_fast:
+            jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh)
+            return WorkList(np.ascontiguousarray(jobs.astype(np.uint32).view(np.int32)), None, pw_max, ph_max, nbytes,
+                            n_launch=int(first.size))
         cover = np.zeros((keys.size, nat.COVER_WORDS), dtype=np.int64)
         o = np.asarray(offs, dtype=np.int64)[seq]
         cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32
         return WorkList(np.ascontiguousarray(items.astype(np.uint32).view(np.int32)),
                         np.ascontiguousarray(cover.astype(np.uint32).view(np.int32)), pw_max, ph_max, nbytes)
+
+
+    def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh) -> np.ndarray:
+        """(block, tile) pairs sorted by (block, blend order) -> fast job records; the first
+        record of every block comes first (they form the grid), the rest is chained by NEXT."""
+        n = keys.size
+        bx0, by0 = (keys % nbx) * bw, (keys // nbx) * bh
+        geo = np.array([[t.x1, t.y1, t.ew, t.eh, t.pw, t.ph] for t in self.tiles], dtype=np.int64)[tids]
+        x1, y1, ew, eh, pw, ph = geo.T
+        desc = self.tile_desc.astype(np.int64)[tids]
+        ox_base, oy_base = bx0 - x1, by0 - y1
+        ix0 = np.zeros(n, np.int64); ix1 = np.zeros(n, np.int64); iy0 = np.zeros(n, np.int64); iy1 = np.zeros(n, np.int64)
+        rows_h = np.zeros(n, np.int64); rows_v = np.zeros(n, np.int64)
+        for key in {(int(a), int(b)) for a, b in zip(pw, ew)}:
+            m = (pw == key[0]) & (ew == key[1])
+            ix0[m] = self._first(key, ox_base[m])
+            ix1[m] = np.minimum(self._first(key, ox_base[m] + bw - 1) + nat.FAST_TAPS, key[0])
+            rows_h[m] = self._tab_packed[key]
+        for key in {(int(a), int(b)) for a, b in zip(ph, eh)}:
+            m = (ph == key[0]) & (eh == key[1])
+            iy0[m] = self._first(key, oy_base[m])
+            iy1[m] = np.minimum(self._first(key, oy_base[m] + bh - 1) + nat.FAST_TAPS, key[0])
+            rows_v[m] = self._tab_packed[key]
+        lead = ix0 & 3
+        J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
+        src = src_off + (iy0 * pw + ix0 - lead) * 3
+        J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_LEAD] = src & 0xFFFFFFFF, src >> 32, lead
+        J[:, nat.J_COLS], J[:, nat.J_ROWS], J[:, nat.J_IX0], J[:, nat.J_IY0] = ix1 - ix0, iy1 - iy0, ix0, iy0
+        J[:, nat.J_ROWS_H], J[:, nat.J_OX_BASE], J[:, nat.J_N_OUT_H] = rows_h, ox_base, ew
+        J[:, nat.J_ROWS_V], J[:, nat.J_OY_BASE], J[:, nat.J_N_OUT_V] = rows_v, oy_base, eh
+        J[:, nat.J_DST_X], J[:, nat.J_DST_Y] = bx0, by0
+        mpitch = desc[:, nat.T_MASK_PITCH]
+        moff = (desc[:, nat.T_MASK_OFF] & 0xFFFFFFFF) + oy_base * mpitch + ox_base          # may be negative
+        J[:, nat.J_OFF_LO], J[:, nat.J_OFF_HI] = moff & 0xFFFFFFFF, moff >> 32
+        cw, chh = np.minimum(bw, self.W - bx0), np.minimum(bh, self.H - by0)
+        X0 = np.maximum(bx0, x1 + desc[:, nat.T_SUP_X0]); X1 = np.minimum(bx0 + cw, x1 + desc[:, nat.T_SUP_X1])
+        Y0 = np.maximum(by0, y1 + desc[:, nat.T_SUP_Y0]); Y1 = np.minimum(by0 + chh, y1 + desc[:, nat.T_SUP_Y1])
+        J[:, nat.J_CX0], J[:, nat.J_CX1], J[:, nat.J_CY0], J[:, nat.J_CY1] = X0 - bx0, X1 - bx0, Y0 - by0, Y1 - by0
+        J[:, nat.J_ROWS_OUT] = Y1 - by0
+        opaque = ((cw == bw) & (chh == bh) & (bx0 >= x1 + desc[:, nat.T_FULL_X0]) & (bx0 + bw <= x1 + desc[:, nat.T_FULL_X1]) &
+                  (by0 >= y1 + desc[:, nat.T_FULL_Y0]) & (by0 + bh <= y1 + desc[:, nat.T_FULL_Y1]))
+        J[:, nat.J_FLAGS] = opaque.astype(np.int64)
+        J[:, nat.J_MPITCH], J[:, nat.J_PITCH] = mpitch, pw * 3
+        frame = ph * pw * 3
+        J[:, nat.J_FRAME_LO], J[:, nat.J_FRAME_HI] = frame & 0xFFFFFFFF, frame >> 32
+        # record order: heads (one per block) first, then the rest; chain through NEXT
+        is_head = np.zeros(n, bool)
+        is_head[first] = True
+        pos = np.empty(n, np.int64)
+        pos[is_head] = np.arange(first.size)
+        pos[~is_head] = first.size + np.arange(n - first.size)
+        nxt = np.full(n, -1, np.int64)
+        same = np.r_[keys[1:] == keys[:-1], False]
+        nxt[same] = pos[1:][same[:-1]]
+        J[:, nat.J_NEXT] = nxt
+        out = np.zeros_like(J)
+        out[pos] = J
+        return out
 
 
 _PLAN_CACHE: Dict[tuple, Plan] = {}

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 2
+#define USDU_ABI_VERSION 3
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -95,6 +95,43 @@ typedef enum usdu_status {
  *   src offset: element offset of the tile's [B][PH][PW][3] processed block in `src`.
  *   Entries of one item are applied in list order (ascending tile id reproduces
  *   upscale/modes/static.py:521-553). */
+
+/* Fast-path job record (USDU_FLAG_FAST): USDU_JOB_WORDS int32, one per (block, tile), built by
+ * the planner so that a CTA needs ONE dependent load before it can start streaming pixels.
+ * With USDU_FLAG_FAST `items_dev` of the two tile kernels holds these records instead of the
+ * generic work items (and `cover_dev` is ignored): the grid is the first n_items records;
+ * further records of the same canvas block are chained through USDU_J_NEXT. */
+#define USDU_JOB_WORDS 32
+#define USDU_J_SRC_A 0     /* crop: canvas px of the first staged column (multiple of 4)
+                              blend: element offset (low 32 bits) of the first staged element, frame 0 */
+#define USDU_J_SRC_B 1     /* crop: canvas row of the first staged row; blend: high 32 bits */
+#define USDU_J_LEAD 2      /* pixels between the staged column 0 and the first needed input pixel (0..3) */
+#define USDU_J_COLS 3      /* needed input pixels */
+#define USDU_J_ROWS 4      /* staged input rows */
+#define USDU_J_IX0 5       /* first needed input pixel / row in axis coordinates */
+#define USDU_J_IY0 6
+#define USDU_J_ROWS_H 7    /* table-pool index of packed row 0 of the horizontal axis */
+#define USDU_J_OX_BASE 8   /* output index of block column 0 (may be negative) */
+#define USDU_J_N_OUT_H 9
+#define USDU_J_ROWS_V 10
+#define USDU_J_OY_BASE 11
+#define USDU_J_N_OUT_V 12
+#define USDU_J_DST_X 13    /* crop: output pixel of block column 0; blend: canvas pixel of block column 0 */
+#define USDU_J_DST_Y 14
+#define USDU_J_OFF_LO 15   /* crop: element offset of the tile's [B][PH][PW][3] block in out */
+#define USDU_J_OFF_HI 16   /* blend: byte offset (signed 64 bit) of block pixel (0,0) in the mask pool */
+#define USDU_J_ROWS_OUT 17 /* crop: valid output rows; blend: rows to run (= CY1) */
+#define USDU_J_COLS_OUT 18 /* crop: valid output pixels */
+#define USDU_J_CX0 19      /* blend: block-relative box outside which this tile leaves the canvas untouched */
+#define USDU_J_CX1 20
+#define USDU_J_CY0 21
+#define USDU_J_CY1 22
+#define USDU_J_FLAGS 23    /* bit 0: the whole block lies in the tile's opaque core (alpha == 255) */
+#define USDU_J_MPITCH 24   /* blend: feather template pitch */
+#define USDU_J_PITCH 25    /* elements per source row (blend) / per output row (crop): PW*3 */
+#define USDU_J_FRAME_LO 26 /* elements per frame PH*PW*3 */
+#define USDU_J_FRAME_HI 27
+#define USDU_J_NEXT 28     /* blend: index of the next record of the same block, -1 = last */
 
 /* Feather-mask spec (host array, USDU_MASK_WORDS int32 each). */
 #define USDU_MASK_WORDS 16

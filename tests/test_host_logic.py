@@ -146,7 +146,7 @@ def test_mask_classes_and_worklists():
     ids = list(range(135))
     wl, offs, total = p.crop_worklist(ids, 1)
     assert total == 135 * 544 * 544 * 3
-    assert p.fast and wl.items.shape == (135 * 5 * 17, nat.CROP_ITEM_WORDS)        # 128 x 32 fast blocks
+    assert p.fast and wl.items.shape == (135 * 5 * 17, nat.JOB_WORDS)              # 128 x 32 fast blocks, job records
     wg, _, _ = p.crop_worklist(ids, 1, use_fast=False)
     assert wg.items.shape == (135 * 9 * 17, nat.CROP_ITEM_WORDS)                    # 64 x 32 generic blocks
     bl = p.blend_worklist(ids, offs, use_fast=False)
@@ -154,6 +154,19 @@ def test_mask_classes_and_worklists():
     for it in bl.items[::997]:                            # cover lists are ascending in tile id
         c = cov[it[2]: it[2] + it[3], 0]
         assert list(c) == sorted(c)
+    # fast job records: heads first, chains cover every (block, tile) pair once, in ascending tile order
+    fj = p.blend_worklist(ids, offs)
+    J = fj.items
+    assert fj.cover is None and fj.n_launch == len({(int(a), int(b)) for a, b in zip(J[:, nat.J_DST_X], J[:, nat.J_DST_Y])})
+    seen = np.zeros(J.shape[0], bool)
+    for h in range(fj.n_launch):
+        i, last = h, -1
+        while i >= 0:
+            assert not seen[i] and (J[i, nat.J_DST_X], J[i, nat.J_DST_Y]) == (J[h, nat.J_DST_X], J[h, nat.J_DST_Y])
+            seen[i] = True
+            i = int(J[i, nat.J_NEXT])
+    assert seen.all()
+    assert (J[:, nat.J_ROWS] <= fj.patch_h).all() and (J[:, nat.J_COLS] <= fj.patch_w).all()
     # every (tile, block) pair with intersecting support is present exactly once
     assert bl.cover.shape[0] == sum(
         ((t.x1 + p.support(t)[2] - 1) // 64 - (t.x1 + p.support(t)[0]) // 64 + 1) *
