@@ -41,6 +41,18 @@ __device__ __forceinline__ float dequant_u8(uint32_t u) {
     return __fdiv_rn(static_cast<float>(u), 255.0f);
 }
 
+// The same value without a divide, a conversion or a table: the byte goes into the mantissa
+// of 2^23 (one LOP), one FADD removes the bias, then q0 = x*rcp, r = fma(-255, q0, x) (exact),
+// q = fma(r, rcp, q0) is the correctly rounded quotient (Markstein); checked for all 256
+// codes against __fdiv_rn in tests/test_gpu_parity.py::test_quantize_dequantize.
+__device__ __forceinline__ float dequant_u8_fast(uint32_t u) {
+    const float x = __uint_as_float(0x4B000000u | u) - 8388608.0f;
+    const float rcp = 0.003921568859368563f;   // fp32(1/255)
+    const float q0 = __fmul_rn(x, rcp);
+    const float r = __fmaf_rn(-255.0f, q0, x);
+    return __fmaf_rn(r, rcp, q0);
+}
+
 __device__ __forceinline__ uint32_t clip8(int v) {
     return static_cast<uint32_t>(min(max(v, 0), 255));
 }

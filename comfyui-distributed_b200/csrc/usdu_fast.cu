@@ -236,7 +236,7 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int64_t pitch, const int3
             BlendOpaque epi;
             epi.dst = cblk;
             epi.pitch = pitch;
-            vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, FBH);
+            vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, J[USDU_J_ROWS_OUT]);
         } else {
             BlendFeather epi;
             epi.dst = cblk;

@@ -45,9 +45,6 @@ quantize_canvas_kernel(const float* __restrict__ img, uint8_t* __restrict__ canv
 __global__ void __launch_bounds__(kThreads)
 dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__ img, int rows, int W3,
                          int64_t pitch, int vec_ok) {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = dequant_u8(i);
-    __syncthreads();
     const int chunks = (W3 + 15) >> 4;
     const int64_t total = (int64_t)rows * chunks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -57,21 +54,21 @@ dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__
         const uint8_t* src = canvas + row * pitch + j0;
         float* dst = img + row * W3 + j0;
         if (vec_ok && j0 + 16 <= W3) {
-            const uint4 v = *reinterpret_cast<const uint4*>(src);
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float4 o;
-                o.x = lut[w[k] & 0xFF];
-                o.y = lut[(w[k] >> 8) & 0xFF];
-                o.z = lut[(w[k] >> 16) & 0xFF];
-                o.w = lut[w[k] >> 24];
+                o.x = dequant_u8_fast(w[k] & 0xFF);
+                o.y = dequant_u8_fast((w[k] >> 8) & 0xFF);
+                o.z = dequant_u8_fast((w[k] >> 16) & 0xFF);
+                o.w = dequant_u8_fast(w[k] >> 24);
                 __stcs(d4 + k, o);
             }
         } else {
             const int n = min(16, W3 - j0);
-            for (int k = 0; k < n; ++k) dst[k] = lut[src[k]];
+            for (int k = 0; k < n; ++k) dst[k] = dequant_u8_fast(src[k]);
         }
     }
 }

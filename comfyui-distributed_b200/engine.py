@@ -117,10 +117,10 @@ class DevicePlan:
             self._wl[key] = (wl, offs, total) + self._upload(wl)
         return self._wl[key]
 
-    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool):
-        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast)
+    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool, B: int = 1):
+        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast, B)
         if key not in self._wl:
-            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast)
+            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast, B)
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
@@ -197,7 +197,7 @@ class Canvas:
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST))
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B)
         if items.shape[0] == 0:
             return
         p = self.plan

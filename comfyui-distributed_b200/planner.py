@@ -347,15 +347,19 @@ class Plan:
         ends = np.minimum(starts + block, n_out) - 1
         return int((sp[ends, 1] - sp[starts, 0]).max())
 
-    def block_shape(self, use_fast: bool) -> Tuple[int, int]:
-        return (nat.FAST_BLOCK_W, nat.FAST_BLOCK_H) if use_fast else (nat.BLOCK_W, nat.BLOCK_H)
+    def block_shape(self, use_fast: bool, n_tile_frames: int = 1 << 30) -> Tuple[int, int]:
+        """Block edge of a launch.  Small launches (few tiles) are latency bound: shorter
+        blocks give the 148 SMs more CTAs to overlap (at the price of more halo rows)."""
+        if not use_fast:
+            return nat.BLOCK_W, nat.BLOCK_H
+        bh = nat.FAST_BLOCK_H if n_tile_frames >= 5 else (16 if n_tile_frames >= 3 else 8)
+        return nat.FAST_BLOCK_W, bh
 
-    def _crop_block_rows(self, t: Tile, use_fast: bool) -> int:
-        """Output rows per crop block.  The fast H pass maps (4-row group, channel) to lanes:
-        keep the staged input rows <= 40 so that 10 groups x 3 channels fill one warp."""
+    def _crop_block_rows(self, t: Tile, use_fast: bool, bh_max: int) -> int:
+        """Output rows per crop block (fast path: keep the staged input rows <= 40)."""
         if not use_fast:
             return nat.BLOCK_H
-        for bh in range(nat.FAST_BLOCK_H, 7, -1):
+        for bh in range(bh_max, 7, -1):
             if self._span_max(t.eh, t.ph, bh, True) <= 40:
                 return bh
         return 8
@@ -366,10 +370,10 @@ class Plan:
         rows = []
         pw_max = ph_max = 1
         nbytes = 0
-        bw, _ = self.block_shape(use_fast)
+        bw, bh_max = self.block_shape(use_fast, len(tile_ids) * B)
         for i, tid in enumerate(tile_ids):
             t = self.tiles[tid]
-            bh = self._crop_block_rows(t, use_fast)
+            bh = self._crop_block_rows(t, use_fast, bh_max)
             ox = np.arange(0, t.pw, bw, dtype=np.int64)
             oy = np.arange(0, t.ph, bh, dtype=np.int64)
             gx, gy = np.meshgrid(ox, oy)
@@ -379,7 +383,7 @@ class Plan:
             it[:, 3], it[:, 4], it[:, 5] = offs[i] & 0xFFFFFFFF, offs[i] >> 32, bh
             rows.append(it)
             pw_max = max(pw_max, self._span_max(t.ew, t.pw, bw, True))
-            ph_max = max(ph_max, self._span_max(t.eh, t.ph, nat.FAST_BLOCK_H if use_fast else bh, True))
+            ph_max = max(ph_max, self._span_max(t.eh, t.ph, bh, True))
             nbytes += t.ew * t.eh * 3 + t.pw * t.ph * 3 * 4      # u8 window read + fp32 tile write
         items = np.concatenate(rows, 0) if rows else np.zeros((0, nat.CROP_ITEM_WORDS), dtype=np.int64)
         if use_fast and items.shape[0]:
@@ -427,11 +431,11 @@ class Plan:
         return J
 
     def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
-                       use_fast: Optional[bool] = None) -> WorkList:
+                       use_fast: Optional[bool] = None, B: int = 1) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
         given order (the order of `tile_ids` IS the blend order)."""
         use_fast = self.fast if use_fast is None else (use_fast and self.fast)
-        bw, bh = self.block_shape(use_fast)
+        bw, bh = self.block_shape(use_fast, len(tile_ids) * B)
         nbx = (self.W + bw - 1) // bw
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1

@@ -53,6 +53,14 @@ def test_quantize_dequantize(B, H, W):
     assert np.array_equal(back.cpu().numpy(), orc.dequantize_u8(got))
 
 
+def test_dequantize_every_code_is_ieee_division():
+    u = np.arange(256, dtype=np.uint8).repeat(48).reshape(1, 16, 256, 3)          # W3 = 768: vector path
+    canvas = torch.from_numpy(u.reshape(1, 16, 768)).to(DEV).contiguous()
+    out = torch.empty((1, 16, 256, 3), dtype=torch.float32, device=DEV)
+    nat.dequantize_canvas(canvas.data_ptr(), out.data_ptr(), 1, 16, 256, 768, _stream())
+    assert np.array_equal(out.cpu().numpy(), u.astype(np.float32) / np.float32(255.0))
+
+
 @pytest.mark.parametrize("n", [0, 1, 15, 16, 4099, 544 * 544 * 3])
 def test_pack_unpack(n):
     rng = np.random.default_rng(n)
