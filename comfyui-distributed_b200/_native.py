@@ -59,6 +59,7 @@ _SIGNATURES = {
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_pack_tiles_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "usdu_unpack_tiles_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "usdu_t0_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p]),
     "usdu_mask_scratch_bytes": (c_int64, [POINTER(c_int32), c_int]),
     "usdu_build_feather_masks": (c_int, [POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
     "usdu_tile_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
@@ -147,6 +148,10 @@ def pack_tiles_u8(src_ptr, dst_ptr, n, stream):
 
 def unpack_tiles_f32(src_ptr, dst_ptr, n, stream):
     _check(lib().usdu_unpack_tiles_f32(src_ptr, dst_ptr, n, stream), "usdu_unpack_tiles_f32")
+
+
+def t0_denoise(tiles_ptr, noise_ptr, out_ptr, n, frame, omd, stream):
+    _check(lib().usdu_t0_denoise(tiles_ptr, noise_ptr, out_ptr, n, frame, omd, stream), "usdu_t0_denoise")
 
 
 def mask_scratch_bytes(specs: np.ndarray) -> int:

@@ -116,7 +116,9 @@ struct CropEpilogue {
     int64_t row_pitch;   // floats per output row
     int ow3;
     const float* lut;
-    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
+    struct Pre {};
+    __device__ __forceinline__ Pre prefetch(int, int) const { return Pre{}; }
+    __device__ __forceinline__ void row(const Pre&, int r, int strip, const uint32_t (&s)[4]) {
         if (4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
             float4 o;
             o.x = lut[s[0]]; o.y = lut[s[1]]; o.z = lut[s[2]]; o.w = lut[s[3]];
@@ -163,7 +165,9 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
 struct BlendOpaque {
     uint8_t* dst;        // canvas block origin
     int64_t pitch;
-    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
+    struct Pre {};
+    __device__ __forceinline__ Pre prefetch(int, int) const { return Pre{}; }
+    __device__ __forceinline__ void row(const Pre&, int r, int strip, const uint32_t (&s)[4]) {
         *reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + 4 * strip) = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
     }
 };
@@ -175,27 +179,35 @@ struct BlendFeather {
     const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
     int mpitch;
     int cx0, cx1;          // sub-rect columns in block pixel coordinates (rows are bounded by the caller)
-    __device__ __forceinline__ void row(int r, int strip, const uint32_t (&s)[4]) {
+    struct Pre {
+        uint32_t aa, ab, dv;   // alpha of the two pixels the 4 bytes touch, canvas word
+        int split;             // bytes [0, split) belong to the first pixel
+    };
+    __device__ __forceinline__ Pre prefetch(int r, int strip) const {
         const int col = 4 * strip;
-        const int pa = col / 3, pb = (col + 3) / 3;          // the 4 bytes touch pixels pa and pb (pb = pa or pa+1)
+        const int pa = col / 3, pb = (col + 3) / 3;          // pb = pa or pa + 1
         const bool ina = pa >= cx0 && pa < cx1, inb = pb >= cx0 && pb < cx1;
-        if (!ina && !inb) return;
         const uint8_t* mrow = mask + (int64_t)r * mpitch;
-        const uint32_t aa = ina ? __ldg(mrow + pa) : 0u;
-        const uint32_t ab = inb ? (pb == pa ? aa : (uint32_t)__ldg(mrow + pb)) : 0u;
-        const int split = 3 * pb - col;                      // bytes [0, split) belong to pa, the rest to pb
-        uint32_t* d = reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + col);
-        if (aa == 255u && ab == 255u) {
+        Pre p;
+        p.aa = ina ? (uint32_t)__ldg(mrow + pa) : 0u;
+        p.ab = inb ? (uint32_t)__ldg(mrow + pb) : 0u;
+        p.split = 3 * pb - col;
+        // the canvas word is needed unless both alphas turn out to be 0 or 255; load it early anyway
+        p.dv = (ina || inb) ? *reinterpret_cast<const uint32_t*>(dst + (int64_t)r * pitch + col) : 0u;
+        return p;
+    }
+    __device__ __forceinline__ void row(const Pre& p, int r, int strip, const uint32_t (&s)[4]) {
+        if ((p.aa | p.ab) == 0u) return;
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + 4 * strip);
+        if ((p.aa & p.ab) == 255u) {
             *d = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
             return;
         }
-        if (aa == 0u && ab == 0u) return;
-        const uint32_t dv = *d;
         uint32_t o = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t a = i < split ? aa : ab;
-            o |= composite8(s[i], (dv >> (8 * i)) & 0xFF, a) << (8 * i);
+            const uint32_t a = i < p.split ? p.aa : p.ab;
+            o |= composite8(s[i], (p.dv >> (8 * i)) & 0xFF, a) << (8 * i);
         }
         *d = o;
     }

@@ -96,7 +96,8 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* 
 
 // ---- V pass: mid -> S values, handed to an epilogue -------------------------------------
 // rows_v: shared-memory copy of the packed rows of block rows 0..FBH-1.
-// Epilogue::row(int block_row, int strip, const uint32_t (&s)[4]).
+// Epilogue::prefetch(block_row, strip) issues the loads the epilogue will need (feather alpha,
+// canvas word) BEFORE the 28 multiply-adds, Epilogue::row(pre, block_row, strip, s) consumes them.
 template <class Epilogue>
 __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int32_t* rows_v, int iy0, Epilogue& epi,
                                       int row_begin, int row_end) {
@@ -109,6 +110,7 @@ __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int
         const int4* rp = reinterpret_cast<const int4*>(rows_v + r * USDU_PACKED_ROW);
         const PackedRow row = unpack_row(rp[0], rp[1]);
         const uint8_t* m = mid + (size_t)(row.first - iy0) * MID_PITCH + 4 * strip;
+        const typename Epilogue::Pre pre = epi.prefetch(r, strip);
         uint32_t w[TAPS];
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) w[t] = *reinterpret_cast<const uint32_t*>(m + (size_t)t * MID_PITCH);
@@ -117,7 +119,7 @@ __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int
         uint32_t s[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) s[q] = finish(acc[q]);
-        epi.row(r, strip, s);
+        epi.row(pre, r, strip, s);
     }
 }
 

@@ -116,6 +116,23 @@ unpack_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int6
     for (int64_t i = (n16 << 4) + tid; i < n; i += stride) dst[i] = lut[src[i]];
 }
 
+// The T0 sampler stand-in of the tests / benchmark as ONE pass: out = clamp(x*omd + nd, 0, 1),
+// every step individually rounded (no FMA contraction) so that it equals the oracle's numpy.
+__global__ void __launch_bounds__(kThreads)
+t0_denoise_kernel(const float4* __restrict__ x, const float4* __restrict__ nd, float4* __restrict__ out,
+                  int64_t n4, int64_t frame4, float omd) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldcs(x + i);
+        const float4 b = __ldg(nd + (i % frame4));
+        float4 o;
+        o.x = fminf(fmaxf(__fadd_rn(__fmul_rn(a.x, omd), b.x), 0.0f), 1.0f);
+        o.y = fminf(fmaxf(__fadd_rn(__fmul_rn(a.y, omd), b.y), 0.0f), 1.0f);
+        o.z = fminf(fmaxf(__fadd_rn(__fmul_rn(a.z, omd), b.z), 0.0f), 1.0f);
+        o.w = fminf(fmaxf(__fadd_rn(__fmul_rn(a.w, omd), b.w), 0.0f), 1.0f);
+        out[i] = o;
+    }
+}
+
 // ======================================================================================
 // shared building blocks of the two resampling kernels
 // ======================================================================================
@@ -474,6 +491,21 @@ int usdu_unpack_tiles_f32(const uint8_t* src_dev, float* dst_dev, int64_t n, voi
     if (n == 0) return USDU_OK;
     const int grid = grid_for(((n >> 4) + kThreads) / kThreads);
     unpack_f32_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src_dev, dst_dev, n);
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+int usdu_t0_denoise(const float* tiles_dev, const float* noise_scaled_dev, float* out_dev, int64_t n, int64_t frame,
+                    float one_minus_d, void* stream) {
+    USDU_REQUIRE(n >= 0 && frame > 0, "usdu_t0_denoise: bad sizes");
+    if (n == 0) return USDU_OK;
+    USDU_REQUIRE(tiles_dev && noise_scaled_dev && out_dev, "usdu_t0_denoise: null pointer");
+    USDU_REQUIRE(n % 4 == 0 && frame % 4 == 0 && n % frame == 0, "usdu_t0_denoise: n and frame must be multiples of 4, n of frame");
+    USDU_REQUIRE((((uintptr_t)tiles_dev | (uintptr_t)noise_scaled_dev | (uintptr_t)out_dev) & 15) == 0, "usdu_t0_denoise: pointers must be 16-byte aligned");
+    const int grid = grid_for((n / 4 + kThreads - 1) / kThreads);
+    t0_denoise_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(tiles_dev), reinterpret_cast<const float4*>(noise_scaled_dev),
+        reinterpret_cast<float4*>(out_dev), n / 4, frame / 4, one_minus_d);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

@@ -183,6 +183,12 @@ int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* 
 /* receiving side of the transport: dst[i] = src[i] / 255.0f (api/job_routes.py:104-132) */
 int usdu_unpack_tiles_f32(const uint8_t* src_dev, float* dst_dev, int64_t n, void* stream);
 
+/* TEST DOUBLE, not part of the reference path: the deterministic T0 sampler stand-in used by the
+ * parity tests and bench.py as one fused pass,
+ * out[i] = clamp(tiles[i]*one_minus_d + noise_scaled[i % frame], 0, 1), each step rounded. */
+int usdu_t0_denoise(const float* tiles_dev, const float* noise_scaled_dev, float* out_dev, int64_t n,
+                    int64_t frame, float one_minus_d, void* stream);
+
 /* Feather templates: n_specs masks into mask_pool_dev.  scratch_dev needs
  * usdu_mask_scratch_bytes(specs, n) bytes. */
 int64_t usdu_mask_scratch_bytes(const int32_t* specs_host, int n_specs);
