@@ -1,6 +1,8 @@
 // usdu_fast.cu -- fast crop+LANCZOS and LANCZOS-back+composite kernels (sm_100a).
 // See usdu_fast.cuh for the engine; this file holds staging, epilogues and launchers.
 #include "usdu_fast.cuh"
+#include "usdu_tma.cuh"
+#include <string.h>
 
 namespace usdu {
 namespace fast {
@@ -87,6 +89,45 @@ __device__ __forceinline__ void stage_f32(uint32_t* __restrict__ in, int xw, con
     }
 }
 
+// TMA path of the crop kernel: the canvas patch arrives row-major in shared memory as two
+// boxes of kBoxB bytes x kBoxR rows (one bulk-tensor load each); this pass re-lays it out planar
+// and row-packed.  Same unit decomposition as stage_u8, LDS instead of LDG.
+constexpr int kBoxB = 256;   // bytes per box row (TMA maximum); 2 boxes cover 15 + 3*(patch_w + 3) bytes
+constexpr int kBoxR = 40;
+// `lead_b` = bytes between the 16-byte aligned box start (a TMA requirement on the inner
+// coordinate, measured: tools/ubench/tma_probe.cu) and the first staged pixel.
+__device__ __forceinline__ void stage_from_raw(uint32_t* __restrict__ in, int xw, const uint8_t* __restrict__ raw,
+                                               int rows, int px_count, int lead, int lead_b) {
+    const int chunks = (px_count + lead + 3) >> 2;
+    const int groups = (rows + 3) >> 2;
+    for (int i = threadIdx.x; i < groups * chunks; i += kT) {
+        const int g = i / chunks, ch = i - g * chunks;
+        uint32_t w[4][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int o = lead_b + 12 * ch + 4 * k;                       // byte offset in the virtual 512-byte row
+            const uint8_t* base = raw + (size_t)(o >> 8) * (kBoxR * kBoxB) + (o & 255);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int rr = min(4 * g + r, rows - 1);
+                w[r][k] = *reinterpret_cast<const uint32_t*>(base + rr * kBoxB);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t t[4];
+            transpose4x4(w[0][k], w[1][k], w[2][k], w[3][k], t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = k * 4 + j;
+                const int px = ch * 4 + col / 3 - lead;
+                const int c = col % 3;
+                if (px >= 0 && px < xw) in[(size_t)(g * 3 + c) * xw + px] = t[j];
+            }
+        }
+    }
+}
+
 // Load the job record of this CTA (thread 0..7 -> one int4 each) and the V-axis rows.
 __device__ __forceinline__ void load_job(int32_t* job_sm, const int32_t* __restrict__ jobs, int idx) {
     if (threadIdx.x < USDU_JOB_WORDS / 4)
@@ -127,25 +168,46 @@ struct CropEpilogue {
     }
 };
 
+// kTma: stage the canvas patch with two cp.async.bulk.tensor.2d loads (UTMALDG) instead of LDG.
+template <bool kTma>
 __global__ void __launch_bounds__(kT, 4)
 crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
-                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int patch_h) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    int32_t* job_sm = reinterpret_cast<int32_t*>(smem);
+                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int patch_h, int W3,
+                 const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job, rows_v] [lut] [bar] [in]
+    const size_t region = kTma ? max(mid_bytes(patch_h), (size_t)2 * kBoxR * kBoxB) : mid_bytes(patch_h);
+    uint8_t* mid = smem;
+    uint8_t* raw = smem;
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem + region);
     int32_t* rows_v = job_sm + USDU_JOB_WORDS;
-    float* lut = reinterpret_cast<float*>(smem + kHeadBytes);
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kHeadBytes + 1024);
-    uint8_t* mid = smem + kHeadBytes + 1024 + in_bytes(patch_w, patch_h);
+    float* lut = reinterpret_cast<float*>(smem + region + kHeadBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + region + kHeadBytes + 1024);
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + region + kHeadBytes + 1024 + 16);
     load_job(job_sm, jobs, blockIdx.x);
-    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8(i);
+    if (kTma && threadIdx.x == 0) tma::mbar_init(bar, 1);
     __syncthreads();
     const JobView J{job_sm};
     const int b = blockIdx.y;
     const int xw = plane_words(patch_w);
+    if (kTma && threadIdx.x == 0) {
+        const int x = (J[USDU_J_SRC_A] * 3) & ~15, y = b * H + J[USDU_J_SRC_B];   // 16-byte aligned box start
+        // second box only when the patch needs it and it starts inside the canvas row
+        const bool two = (J[USDU_J_SRC_A] * 3 - x) + (J[USDU_J_COLS] + J[USDU_J_LEAD]) * 3 > kBoxB && x + kBoxB < W3;
+        tma::mbar_expect_tx(bar, (two ? 2 : 1) * kBoxR * kBoxB);
+        tma::load_2d(raw, &cmap, x, y, bar);
+        if (two) tma::load_2d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, bar);
+    }
+    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
     const PackedRow rh = load_row_h(tabs, J);
     stage_rows_v(rows_v, tabs, J);
-    const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
-    stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
+    if (kTma) {
+        tma::mbar_wait(bar, 0);
+        stage_from_raw(in, xw, raw, J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD], (J[USDU_J_SRC_A] * 3) & 15);
+    } else {
+        const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
+        stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
+    }
     __syncthreads();
     hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
     __syncthreads();
@@ -262,7 +324,10 @@ blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int64_t pitch, const int3
     }
 }
 
-static size_t crop_smem(int patch_w, int patch_h) { return kHeadBytes + 1024 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t crop_smem(int patch_w, int patch_h, bool use_tma) {
+    const size_t region = use_tma ? max(mid_bytes(patch_h), (size_t)2 * kBoxR * kBoxB) : mid_bytes(patch_h);
+    return region + kHeadBytes + 1024 + 16 + in_bytes(patch_w, patch_h);
+}
 static size_t blend_smem(int patch_w, int patch_h) { return kHeadBytes + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
 
 static int optin(const void* fn, size_t bytes) {
@@ -276,10 +341,19 @@ static int optin(const void* fn, size_t bytes) {
 
 int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
                 const int32_t* items, int n_items, int patch_w, int patch_h, float* out, cudaStream_t st) {
-    const size_t smem = crop_smem(patch_w, patch_h);
-    int s = optin((const void*)crop_fast_kernel, smem);
+    // TMA staging needs the patch to fit two kBoxB x kBoxR boxes (always true for scales <= ~1.2)
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    bool use_tma = patch_h <= kBoxR && 15 + (patch_w + 3) * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
+    if (use_tma) use_tma = tma::encode_u8_2d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)pitch, kBoxB, kBoxR);
+    const size_t smem = crop_smem(patch_w, patch_h, use_tma);
+    const void* fn = use_tma ? (const void*)crop_fast_kernel<true> : (const void*)crop_fast_kernel<false>;
+    int s = optin(fn, smem);
     if (s != USDU_OK) return s;
-    crop_fast_kernel<<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h);
+    if (use_tma)
+        crop_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap);
+    else
+        crop_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
