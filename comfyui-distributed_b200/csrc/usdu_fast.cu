@@ -191,12 +191,12 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
     const int b = blockIdx.y;
     const int xw = plane_words(patch_w);
     if (kTma && threadIdx.x == 0) {
-        const int x = (J[USDU_J_SRC_A] * 3) & ~15, y = b * H + J[USDU_J_SRC_B];   // 16-byte aligned box start
+        const int x = (J[USDU_J_SRC_A] * 3) & ~15, y = J[USDU_J_SRC_B];           // 16-byte aligned box start
         // second box only when the patch needs it and it starts inside the canvas row
         const bool two = (J[USDU_J_SRC_A] * 3 - x) + (J[USDU_J_COLS] + J[USDU_J_LEAD]) * 3 > kBoxB && x + kBoxB < W3;
         tma::mbar_expect_tx(bar, (two ? 2 : 1) * kBoxR * kBoxB);
-        tma::load_2d(raw, &cmap, x, y, bar);
-        if (two) tma::load_2d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, bar);
+        tma::load_3d(raw, &cmap, x, y, b, bar);
+        if (two) tma::load_3d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, b, bar);
     }
     for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
     const PackedRow rh = load_row_h(tabs, J);
@@ -223,27 +223,42 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
 // ======================================================================================
 // blend
 // ======================================================================================
+// The canvas block (128 px x bh rows) lives in shared memory for the whole CTA: it arrives with
+// two bulk-tensor loads (UTMALDG, 192-byte wide boxes), every tile of the block composites into
+// it, and it leaves with two bulk-tensor stores (UTMASTG).  The canvas is read and written once
+// per block regardless of how many tiles overlap there, and the epilogue has no global access
+// except the feather template.
+constexpr int kDBox = FBW * 3 / 2;          // 192 bytes per box row
+
+struct DTile {
+    uint8_t* base;
+    int bh;                                  // rows per box
+    __device__ __forceinline__ uint32_t* word(int r, int strip) const {
+        const int col = 4 * strip;
+        const int box = col >= kDBox ? 1 : 0;
+        return reinterpret_cast<uint32_t*>(base + (size_t)box * bh * kDBox + r * kDBox + (col - box * kDBox));
+    }
+};
+
 // interior of a tile (alpha == 255 over the whole block): the canvas block becomes S
 struct BlendOpaque {
-    uint8_t* dst;        // canvas block origin
-    int64_t pitch;
+    DTile d;
     struct Pre {};
     __device__ __forceinline__ Pre prefetch(int, int) const { return Pre{}; }
     __device__ __forceinline__ void row(const Pre&, int r, int strip, const uint32_t (&s)[4]) {
-        *reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + 4 * strip) = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
+        *d.word(r, strip) = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
     }
 };
 
 // general case: per-pixel alpha from the feather template, zero outside the tile's sub-rect
 struct BlendFeather {
-    uint8_t* dst;
-    int64_t pitch;
+    DTile d;
     const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
     int mpitch;
     int cx0, cx1;          // sub-rect columns in block pixel coordinates (rows are bounded by the caller)
     struct Pre {
-        uint32_t aa, ab, dv;   // alpha of the two pixels the 4 bytes touch, canvas word
-        int split;             // bytes [0, split) belong to the first pixel
+        uint32_t aa, ab;   // alpha of the two pixels the 4 bytes touch
+        int split;         // bytes [0, split) belong to the first pixel
     };
     __device__ __forceinline__ Pre prefetch(int r, int strip) const {
         const int col = 4 * strip;
@@ -254,73 +269,96 @@ struct BlendFeather {
         p.aa = ina ? (uint32_t)__ldg(mrow + pa) : 0u;
         p.ab = inb ? (uint32_t)__ldg(mrow + pb) : 0u;
         p.split = 3 * pb - col;
-        // the canvas word is needed unless both alphas turn out to be 0 or 255; load it early anyway
-        p.dv = (ina || inb) ? *reinterpret_cast<const uint32_t*>(dst + (int64_t)r * pitch + col) : 0u;
         return p;
     }
     __device__ __forceinline__ void row(const Pre& p, int r, int strip, const uint32_t (&s)[4]) {
         if ((p.aa | p.ab) == 0u) return;
-        uint32_t* d = reinterpret_cast<uint32_t*>(dst + (int64_t)r * pitch + 4 * strip);
+        uint32_t* w = d.word(r, strip);
         if ((p.aa & p.ab) == 255u) {
-            *d = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
+            *w = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
             return;
         }
+        const uint32_t dv = *w;
         uint32_t o = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t a = i < p.split ? p.aa : p.ab;
-            o |= composite8(s[i], (p.dv >> (8 * i)) & 0xFF, a) << (8 * i);
+            o |= composite8(s[i], (dv >> (8 * i)) & 0xFF, a) << (8 * i);
         }
-        *d = o;
+        *w = o;
     }
 };
 
 template <bool kSrcU8>
 __global__ void __launch_bounds__(kT, 4)
-blend_fast_kernel(uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
-                  const uint8_t* __restrict__ mask_pool, const int32_t* __restrict__ jobs,
-                  const void* __restrict__ src_v, int patch_w, int patch_h) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    int32_t* job_sm = reinterpret_cast<int32_t*>(smem);
+blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
+                  const int32_t* __restrict__ jobs, const void* __restrict__ src_v, int W3, int patch_w, int patch_h,
+                  int block_rows, const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [canvas block: 2 boxes x block_rows x 192] [job, rows_v] [bar] [in] [mid]
+    const size_t dbytes = (size_t)2 * block_rows * kDBox;
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem + dbytes);
     int32_t* rows_v = job_sm + USDU_JOB_WORDS;
-    uint32_t* in = reinterpret_cast<uint32_t*>(smem + kHeadBytes);
-    uint8_t* mid = smem + kHeadBytes + in_bytes(patch_w, patch_h);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dbytes + kHeadBytes);
+    uint32_t* in = reinterpret_cast<uint32_t*>(smem + dbytes + kHeadBytes + 16);
+    uint8_t* mid = smem + dbytes + kHeadBytes + 16 + in_bytes(patch_w, patch_h);
     const int b = blockIdx.y;
     const int xw = plane_words(patch_w);
     const JobView J{job_sm};
+    DTile D{smem, block_rows};
     int idx = blockIdx.x;
+    load_job(job_sm, jobs, idx);
+    if (threadIdx.x == 0) tma::mbar_init(bar, 1);
+    __syncthreads();
+    const int bx3 = J[USDU_J_DST_X] * 3, by = J[USDU_J_DST_Y];
+    const bool two = bx3 + kDBox < W3;         // the right half exists (a box may not START past the row end)
+    if (threadIdx.x == 0) {                    // canvas block -> shared, asynchronously
+        tma::mbar_expect_tx(bar, (uint32_t)(two ? dbytes : dbytes / 2));
+        tma::load_3d(smem, &cmap, bx3, by, b, bar);
+        if (two) tma::load_3d(smem + (size_t)block_rows * kDBox, &cmap, bx3 + kDBox, by, b, bar);
+    }
+    bool first = true;
     while (idx >= 0) {
-        __syncthreads();                       // the previous tile's passes are done with job / rows / in / mid
-        load_job(job_sm, jobs, idx);
-        __syncthreads();
+        if (!first) {
+            __syncthreads();                   // the previous tile's passes are done with job / rows / in / mid
+            load_job(job_sm, jobs, idx);
+            __syncthreads();
+        }
         const PackedRow rh = load_row_h(tabs, J);
         stage_rows_v(rows_v, tabs, J);
-        const int64_t first = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
+        const int64_t first_el = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
         if (kSrcU8)
-            stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+            stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
                      J[USDU_J_COLS], J[USDU_J_LEAD]);
         else
-            stage_f32(in, xw, static_cast<const float*>(src_v) + first, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+            stage_f32(in, xw, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
                       J[USDU_J_COLS], J[USDU_J_LEAD]);
         __syncthreads();
         hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
         __syncthreads();
-        uint8_t* cblk = canvas + ((int64_t)b * H + J[USDU_J_DST_Y]) * pitch + (int64_t)J[USDU_J_DST_X] * 3;
+        if (first) tma::mbar_wait(bar, 0);     // the canvas block has landed
         if (J[USDU_J_FLAGS] & 1) {
             BlendOpaque epi;
-            epi.dst = cblk;
-            epi.pitch = pitch;
+            epi.d = D;
             vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, J[USDU_J_ROWS_OUT]);
         } else {
             BlendFeather epi;
-            epi.dst = cblk;
-            epi.pitch = pitch;
+            epi.d = D;
             epi.mpitch = J[USDU_J_MPITCH];
             epi.mask = mask_pool + J.i64(USDU_J_OFF_LO);
             epi.cx0 = J[USDU_J_CX0]; epi.cx1 = J[USDU_J_CX1];
             vpass(mid, rows_v, J[USDU_J_IY0], epi, J[USDU_J_CY0], J[USDU_J_CY1]);
         }
         idx = J[USDU_J_NEXT];
+        first = false;
+    }
+    tma::fence_async_smem();                   // generic-proxy writes of the block -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::store_3d(&cmap, bx3, by, b, smem);
+        if (two) tma::store_3d(&cmap, bx3 + kDBox, by, b, smem + (size_t)block_rows * kDBox);
+        tma::store_commit();
+        tma::store_wait_all();
     }
 }
 
@@ -328,7 +366,9 @@ static size_t crop_smem(int patch_w, int patch_h, bool use_tma) {
     const size_t region = use_tma ? max(mid_bytes(patch_h), (size_t)2 * kBoxR * kBoxB) : mid_bytes(patch_h);
     return region + kHeadBytes + 1024 + 16 + in_bytes(patch_w, patch_h);
 }
-static size_t blend_smem(int patch_w, int patch_h) { return kHeadBytes + in_bytes(patch_w, patch_h) + mid_bytes(patch_h); }
+static size_t blend_smem(int patch_w, int patch_h, int block_rows) {
+    return (size_t)2 * block_rows * kDBox + kHeadBytes + 16 + in_bytes(patch_w, patch_h) + mid_bytes(patch_h);
+}
 
 static int optin(const void* fn, size_t bytes) {
     if (bytes > 227 * 1024) {
@@ -345,7 +385,7 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
     CUtensorMap cmap;
     memset(&cmap, 0, sizeof(cmap));
     bool use_tma = patch_h <= kBoxR && 15 + (patch_w + 3) * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
-    if (use_tma) use_tma = tma::encode_u8_2d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)pitch, kBoxB, kBoxR);
+    if (use_tma) use_tma = tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kBoxB, kBoxR);
     const size_t smem = crop_smem(patch_w, patch_h, use_tma);
     const void* fn = use_tma ? (const void*)crop_fast_kernel<true> : (const void*)crop_fast_kernel<false>;
     int s = optin(fn, smem);
@@ -360,15 +400,26 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
 
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
                  const uint8_t* mask_pool, const int32_t* items, int n_items, const int32_t* cover, int patch_w,
-                 int patch_h, const void* src, int src_is_u8, cudaStream_t st) {
-    const size_t smem = blend_smem(patch_w, patch_h);
+                 int patch_h, const void* src, int src_is_u8, int block_rows, cudaStream_t st) {
+    if (block_rows <= 0 || block_rows > FBH) {
+        set_error("usdu_tile_blend: fast path needs the block height (1..%d) in flags bits 8..15, got %d", FBH, block_rows);
+        return USDU_ERR_INVALID;
+    }
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    if (((uintptr_t)canvas & 15) != 0 ||
+        !tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kDBox, block_rows)) {
+        set_error("usdu_tile_blend: cannot build the canvas tensor map (cuTensorMapEncodeTiled)");
+        return USDU_ERR_CUDA;
+    }
+    const size_t smem = blend_smem(patch_w, patch_h, block_rows);
     const void* fn = src_is_u8 ? (const void*)blend_fast_kernel<true> : (const void*)blend_fast_kernel<false>;
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (src_is_u8)
-        blend_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, mask_pool, items, src, patch_w, patch_h);
+        blend_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap);
     else
-        blend_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, mask_pool, items, src, patch_w, patch_h);
+        blend_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

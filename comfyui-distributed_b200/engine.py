@@ -203,12 +203,13 @@ class Canvas:
         p = self.plan
         src = src.contiguous()
         n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
+        flags = self.flags | (wl.block_rows << 8)
         cover_ptr = cover.data_ptr() if cover is not None else 0
         _launch("blend", wl.algo_bytes * self.B,
                 lambda: nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
                                        self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(),
                                        n_grid, cover_ptr, wl.patch_w, wl.patch_h, src.data_ptr(),
-                                       src_u8, self.flags, _stream_ptr()))
+                                       src_u8, flags, _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
 

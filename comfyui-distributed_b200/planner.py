@@ -117,6 +117,7 @@ class WorkList:
     patch_h: int
     algo_bytes: int                   # algorithmic HBM bytes of the launch per frame
     n_launch: int = -1                # grid size when it differs from len(items) (chained fast jobs)
+    block_rows: int = 0               # canvas block height of a fast blend launch
 
 
 @dataclass
@@ -470,7 +471,7 @@ class Plan:
         if use_fast:
             jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh)
             return WorkList(np.ascontiguousarray(jobs.astype(np.uint32).view(np.int32)), None, pw_max, ph_max, nbytes,
-                            n_launch=int(first.size))
+                            n_launch=int(first.size), block_rows=bh)
         cover = np.zeros((keys.size, nat.COVER_WORDS), dtype=np.int64)
         o = np.asarray(offs, dtype=np.int64)[seq]
         cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32
