@@ -295,12 +295,15 @@ def main():
     peak, peak_src = measured_peak_gbs()
     dom = "blend"
     k = kern.get(dom, {"gbps": 0.0, "launches": 0, "avg_us": 0.0, "bytes": 0})
-    traffic = None
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "r01_blend_traffic.json")
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_note = f"ncu --set full, {tj.get('launch')}: {tj.get('duration_us')} us, algorithmic 43.1 MB (profiles/r01_blend_traffic.json)"
     roofline = {"bound": "hbm", "kernel": "usdu::fast::blend_fast_kernel", "achieved": round(k["gbps"], 1), "peak": peak,
-                "unit": "GB/s", "frac": round(k["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(k["gbps"] / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peak_src,
                 "launches_per_step": k["launches"], "avg_launch_us": round(k["avg_us"], 2),
                 "algorithmic_bytes_per_step": k["bytes"],
                 "timing": "CUDA events around every launch of the last timed step (event-record nodes inside the wave graph)",
