@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 3
+ABI_VERSION = 4
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -37,7 +37,7 @@ FAST_TAPS = 7
 JOB_WORDS = 32
 (J_SRC_A, J_SRC_B, J_LEAD, J_COLS, J_ROWS, J_IX0, J_IY0, J_ROWS_H, J_OX_BASE, J_N_OUT_H, J_ROWS_V, J_OY_BASE, J_N_OUT_V,
  J_DST_X, J_DST_Y, J_OFF_LO, J_OFF_HI, J_ROWS_OUT, J_COLS_OUT, J_CX0, J_CX1, J_CY0, J_CY1, J_FLAGS, J_MPITCH, J_PITCH,
- J_FRAME_LO, J_FRAME_HI, J_NEXT) = range(29)
+ J_FRAME_LO, J_FRAME_HI, J_NEXT, J_TAPS_H, J_TAPS_V) = range(31)
 
 
 class NativeError(RuntimeError):
@@ -117,11 +117,13 @@ def build_resample_table(in_size: int, out_size: int) -> np.ndarray:
         _check(int(words), "usdu_resample_table_words")
     tab = np.zeros(int(words), dtype=np.int32)
     _check(L.usdu_build_resample_table(in_size, out_size, _i32p(tab)), "usdu_build_resample_table")
-    return tab
+    if tab[4]:                                   # trim the packed section to its actual row stride
+        tab = tab[: int(tab[4]) + out_size * int(tab[6])]
+    return np.ascontiguousarray(tab)
 
 
 def build_identity_table(size: int) -> np.ndarray:
-    tab = np.zeros(TAB_HEADER + size * (3 + PACKED_ROW), dtype=np.int32)
+    tab = np.zeros(((TAB_HEADER + 3 * size + 3) & ~3) + size * PACKED_ROW, dtype=np.int32)
     _check(lib().usdu_build_identity_table(size, _i32p(tab)), "usdu_build_identity_table")
     return tab
 

@@ -136,17 +136,45 @@ __device__ __forceinline__ void load_job(int32_t* job_sm, const int32_t* __restr
 }
 
 __device__ __forceinline__ void stage_rows_v(int32_t* rows_sm, const int32_t* __restrict__ tabs, const JobView& J) {
-    if (threadIdx.x < FBH * 2) {
-        const int o = clampi(J[USDU_J_OY_BASE] + (threadIdx.x >> 1), 0, J[USDU_J_N_OUT_V] - 1);
-        reinterpret_cast<int4*>(rows_sm)[threadIdx.x] =
-            __ldg(reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_V] + (size_t)o * USDU_PACKED_ROW) + (threadIdx.x & 1));
+    const int q = (J[USDU_J_TAPS_V] + 1) / 4;                        // int4 per packed row: 2 or 4
+    for (int i = threadIdx.x; i < FBH * q; i += kT) {
+        const int r = i / q, part = i - r * q;
+        const int o = clampi(J[USDU_J_OY_BASE] + r, 0, J[USDU_J_N_OUT_V] - 1);
+        reinterpret_cast<int4*>(rows_sm)[i] =
+            __ldg(reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_V] + (size_t)o * (4 * q)) + part);
     }
 }
 
-__device__ __forceinline__ PackedRow load_row_h(const int32_t* __restrict__ tabs, const JobView& J) {
+template <int TAPS>
+__device__ __forceinline__ PackedRow<TAPS> load_row_h(const int32_t* __restrict__ tabs, const JobView& J) {
     const int o = clampi(J[USDU_J_OX_BASE] + (int)(threadIdx.x % FBW), 0, J[USDU_J_N_OUT_H] - 1);
-    const int4* p = reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_H] + (size_t)o * USDU_PACKED_ROW);
-    return unpack_row(__ldg(p), __ldg(p + 1));
+    const int4* p = reinterpret_cast<const int4*>(tabs + J[USDU_J_ROWS_H] + (size_t)o * (TAPS + 1));
+    return read_row<TAPS>([&](int i) { return __ldg(p + i); });
+}
+
+// stage -> (sync) -> H pass for one job; the tap count of the axis picks the instantiation
+template <class Stage>
+__device__ __forceinline__ void stage_and_hpass(const int32_t* __restrict__ tabs, const JobView& J, uint32_t* in, uint8_t* mid,
+                                                int xw, Stage stage) {
+    if (J[USDU_J_TAPS_H] <= USDU_FAST_TAPS) {
+        const PackedRow<USDU_FAST_TAPS> rh = load_row_h<USDU_FAST_TAPS>(tabs, J);    // in flight during staging
+        stage();
+        __syncthreads();
+        hpass<USDU_FAST_TAPS>(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+    } else {
+        const PackedRow<MAXTAPS> rh = load_row_h<MAXTAPS>(tabs, J);
+        stage();
+        __syncthreads();
+        hpass<MAXTAPS>(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+    }
+}
+
+template <class Epilogue>
+__device__ __forceinline__ void vpass_any(const uint8_t* mid, const int32_t* rows_v, const JobView& J, Epilogue& epi, int r0, int r1) {
+    if (J[USDU_J_TAPS_V] <= USDU_FAST_TAPS)
+        vpass<USDU_FAST_TAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
+    else
+        vpass<MAXTAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
 }
 
 // ======================================================================================
@@ -199,17 +227,17 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
         if (two) tma::load_3d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, b, bar);
     }
     for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
-    const PackedRow rh = load_row_h(tabs, J);
     stage_rows_v(rows_v, tabs, J);
-    if (kTma) {
-        tma::mbar_wait(bar, 0);
-        stage_from_raw(in, xw, raw, J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD], (J[USDU_J_SRC_A] * 3) & 15);
-    } else {
-        const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
-        stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
-    }
-    __syncthreads();
-    hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+    stage_and_hpass(tabs, J, in, mid, xw, [&]() {
+        if (kTma) {
+            tma::mbar_wait(bar, 0);
+            stage_from_raw(in, xw, raw, J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD], (J[USDU_J_SRC_A] * 3) & 15);
+            __syncthreads();               // raw (aliased with mid) is consumed before the H pass overwrites it
+        } else {
+            const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
+            stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
+        }
+    });
     __syncthreads();
     CropEpilogue epi;
     epi.row_pitch = J[USDU_J_PITCH];
@@ -217,7 +245,7 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
               (int64_t)J[USDU_J_DST_X] * 3;
     epi.ow3 = J[USDU_J_COLS_OUT] * 3;
     epi.lut = lut;
-    vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, J[USDU_J_ROWS_OUT]);
+    vpass_any(mid, rows_v, J, epi, 0, J[USDU_J_ROWS_OUT]);
 }
 
 // ======================================================================================
@@ -324,30 +352,29 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
             load_job(job_sm, jobs, idx);
             __syncthreads();
         }
-        const PackedRow rh = load_row_h(tabs, J);
         stage_rows_v(rows_v, tabs, J);
         const int64_t first_el = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
-        if (kSrcU8)
-            stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
-                     J[USDU_J_COLS], J[USDU_J_LEAD]);
-        else
-            stage_f32(in, xw, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
-                      J[USDU_J_COLS], J[USDU_J_LEAD]);
-        __syncthreads();
-        hpass(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+        stage_and_hpass(tabs, J, in, mid, xw, [&]() {
+            if (kSrcU8)
+                stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+                         J[USDU_J_COLS], J[USDU_J_LEAD]);
+            else
+                stage_f32(in, xw, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
+                          J[USDU_J_COLS], J[USDU_J_LEAD]);
+        });
         __syncthreads();
         if (first) tma::mbar_wait(bar, 0);     // the canvas block has landed
         if (J[USDU_J_FLAGS] & 1) {
             BlendOpaque epi;
             epi.d = D;
-            vpass(mid, rows_v, J[USDU_J_IY0], epi, 0, J[USDU_J_ROWS_OUT]);
+            vpass_any(mid, rows_v, J, epi, 0, J[USDU_J_ROWS_OUT]);
         } else {
             BlendFeather epi;
             epi.d = D;
             epi.mpitch = J[USDU_J_MPITCH];
             epi.mask = mask_pool + J.i64(USDU_J_OFF_LO);
             epi.cx0 = J[USDU_J_CX0]; epi.cx1 = J[USDU_J_CX1];
-            vpass(mid, rows_v, J[USDU_J_IY0], epi, J[USDU_J_CY0], J[USDU_J_CY1]);
+            vpass_any(mid, rows_v, J, epi, J[USDU_J_CY0], J[USDU_J_CY1]);
         }
         idx = J[USDU_J_NEXT];
         first = false;

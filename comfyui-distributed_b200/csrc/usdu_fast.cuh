@@ -28,19 +28,29 @@ namespace fast {
 constexpr int kT = 256;                    // threads per CTA: 2 sub-groups of FBW threads
 constexpr int FBW = USDU_FAST_BLOCK_W;     // 128-pixel wide blocks
 constexpr int FBH = USDU_FAST_BLOCK_H;     // up to 32 rows
-constexpr int TAPS = USDU_FAST_TAPS;       // 7
+constexpr int MAXTAPS = USDU_FAST_TAPS_WIDE;   // 15: the wide variant, picked per job and axis
 constexpr int R = 4;                       // independent lines (rows / byte columns) per thread
 constexpr int MID_PITCH = FBW * 3 + 4;     // 388 bytes: 4 consecutive rows land 4 banks apart
 
-struct PackedRow {  // one output of an axis: first input index + 7 coefficients (32 bytes)
+// one output of an axis: first input index + TAPS coefficients (TAPS + 1 int32, 16-byte aligned)
+template <int TAPS>
+struct PackedRow {
     int first;
     int k[TAPS];
 };
 
-__device__ __forceinline__ PackedRow unpack_row(const int4 a, const int4 b) {
-    PackedRow r;
-    r.first = a.x; r.k[0] = a.y; r.k[1] = a.z; r.k[2] = a.w;
-    r.k[3] = b.x; r.k[4] = b.y; r.k[5] = b.z; r.k[6] = b.w;
+template <int TAPS, class LoadInt4>
+__device__ __forceinline__ PackedRow<TAPS> read_row(LoadInt4 ld) {
+    PackedRow<TAPS> r;
+    int v[TAPS + 1];
+#pragma unroll
+    for (int i = 0; i < (TAPS + 1) / 4; ++i) {
+        const int4 q = ld(i);
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+    r.first = v[0];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) r.k[t] = v[t + 1];
     return r;
 }
 
@@ -51,8 +61,9 @@ __device__ __forceinline__ uint32_t finish(int acc) {
     return (uint32_t)__vimin_s32_relu(acc >> kPrecisionBits, 255);
 }
 
-// 4 lines x 7 taps: words w[t] hold the 4 lines' bytes of tap t
-__device__ __forceinline__ void dot4(const uint32_t (&w)[TAPS], const PackedRow& row, int (&acc)[R]) {
+// 4 lines x TAPS taps: words w[t] hold the 4 lines' bytes of tap t
+template <int TAPS>
+__device__ __forceinline__ void dot4(const uint32_t (&w)[TAPS], const PackedRow<TAPS>& row, int (&acc)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 1 << (kPrecisionBits - 1);
 #pragma unroll
@@ -73,7 +84,8 @@ struct JobView {
 
 // ---- H pass: in (planar, row packed) -> mid[row][block px * 3 + c] ----------------------
 // `row` = this thread's pixel column coefficients (loaded from global before staging).
-__device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const PackedRow& row,
+template <int TAPS>
+__device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const PackedRow<TAPS>& row,
                                       int ix0, int rows_in, int xw) {
     const int px = threadIdx.x % FBW, sub = threadIdx.x / FBW;
     const uint32_t* w0 = in + (row.first - ix0);
@@ -96,9 +108,9 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* 
 
 // ---- V pass: mid -> S values, handed to an epilogue -------------------------------------
 // rows_v: shared-memory copy of the packed rows of block rows 0..FBH-1.
-// Epilogue::prefetch(block_row, strip) issues the loads the epilogue will need (feather alpha,
-// canvas word) BEFORE the 28 multiply-adds, Epilogue::row(pre, block_row, strip, s) consumes them.
-template <class Epilogue>
+// Epilogue::prefetch(block_row, strip) issues the loads the epilogue will need (feather alpha)
+// BEFORE the multiply-adds, Epilogue::row(pre, block_row, strip, s) consumes them.
+template <int TAPS, class Epilogue>
 __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int32_t* rows_v, int iy0, Epilogue& epi,
                                       int row_begin, int row_end) {
     constexpr int STRIPS = FBW * 3 / 4;             // 96
@@ -107,8 +119,8 @@ __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int
     for (int it = threadIdx.x; it < total; it += kT) {
         const int rr = it / STRIPS, strip = it - rr * STRIPS;
         const int r = row_begin + rr;
-        const int4* rp = reinterpret_cast<const int4*>(rows_v + r * USDU_PACKED_ROW);
-        const PackedRow row = unpack_row(rp[0], rp[1]);
+        const int4* rp = reinterpret_cast<const int4*>(rows_v + r * (TAPS + 1));
+        const PackedRow<TAPS> row = read_row<TAPS>([&](int i) { return rp[i]; });
         const uint8_t* m = mid + (size_t)(row.first - iy0) * MID_PITCH + 4 * strip;
         const typename Epilogue::Pre pre = epi.prefetch(r, strip);
         uint32_t w[TAPS];
@@ -124,7 +136,7 @@ __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int
 }
 
 // Shared-memory sizing shared by host and device.
-__host__ __device__ inline int plane_words(int patch_w) { return patch_w + TAPS + 1; }
+__host__ __device__ inline int plane_words(int patch_w) { return patch_w + MAXTAPS + 1; }
 __host__ __device__ inline int in_groups(int patch_h) { return (patch_h + 3) / 4; }
 __host__ __device__ inline size_t in_bytes(int patch_w, int patch_h) {
     return (size_t)in_groups(patch_h) * 3 * plane_words(patch_w) * 4;
@@ -132,7 +144,7 @@ __host__ __device__ inline size_t in_bytes(int patch_w, int patch_h) {
 __host__ __device__ inline size_t mid_bytes(int patch_h) {
     return ((size_t)((patch_h + 3) / 4 * 4 + 1) * MID_PITCH + 15) / 16 * 16;
 }
-constexpr size_t kHeadBytes = USDU_JOB_WORDS * 4 + (size_t)FBH * USDU_PACKED_ROW * 4;   // job record + rows_v
+constexpr size_t kHeadBytes = USDU_JOB_WORDS * 4 + (size_t)FBH * (MAXTAPS + 1) * 4;   // job record + rows_v
 
 }  // namespace fast
 }  // namespace usdu

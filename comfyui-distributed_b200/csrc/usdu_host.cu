@@ -77,7 +77,8 @@ int usdu_resample_ksize(int in_size, int out_size) {
 int64_t usdu_resample_table_words(int in_size, int out_size) {
     int ks = usdu_resample_ksize(in_size, out_size);
     if (ks < 0) return ks;
-    return (int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks) + (int64_t)out_size * USDU_PACKED_ROW;
+    // the packed rows are read with 128-bit loads: their start is padded to 4 int32
+    return (((int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks) + 3) & ~(int64_t)3) + (int64_t)out_size * 2 * USDU_PACKED_ROW;
 }
 
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
@@ -125,7 +126,8 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
     // Packed rows for the fast kernels: {first input index, k0..k6}, usable when no output
     // needs more than USDU_FAST_TAPS taps and any USDU_FAST_GROUP consecutive outputs read at
     // most USDU_FAST_WINDOW consecutive inputs.
-    int32_t* packed = kk + (int64_t)out_size * ksize;
+    int32_t* packed = table + (((int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ksize) + 3) & ~(int64_t)3);
+    for (int32_t* q = kk + (int64_t)out_size * ksize; q < packed; ++q) *q = 0;
     int tmax = 0, span = 0;
     for (int xx = 0; xx < out_size; xx++) {
         if (bounds[xx * 2 + 1] > tmax) tmax = bounds[xx * 2 + 1];
@@ -135,12 +137,14 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
     }
     table[3] = tmax;
     table[5] = span;
-    const bool fast = tmax <= USDU_FAST_TAPS;
+    const bool fast = tmax <= USDU_FAST_TAPS_WIDE;
+    const int stride = tmax <= USDU_FAST_TAPS ? USDU_PACKED_ROW : 2 * USDU_PACKED_ROW;
     table[4] = fast ? (int32_t)(packed - table) : 0;
+    table[6] = stride;
     for (int xx = 0; xx < out_size; xx++) {
-        int32_t* r = packed + (int64_t)xx * USDU_PACKED_ROW;
+        int32_t* r = packed + (int64_t)xx * stride;
         r[0] = bounds[xx * 2];
-        for (int t = 0; t < USDU_FAST_TAPS; ++t)
+        for (int t = 0; t < stride - 1; ++t)
             r[1 + t] = (fast && t < bounds[xx * 2 + 1]) ? kk[(int64_t)xx * ksize + t] : 0;
     }
     return USDU_OK;
@@ -151,10 +155,11 @@ int usdu_build_identity_table(int size, int32_t* table) {
     // Pillow skips a pass whose axis keeps its size (Resample.c ImagingResampleInner); one tap
     // of weight 2^22 reproduces that exactly: (v * 2^22 + 2^21) >> 22 == v.
     table[0] = size; table[1] = size; table[2] = 1; table[3] = 1;
-    table[4] = USDU_TAB_HEADER + 3 * size; table[5] = USDU_FAST_GROUP - 1 + USDU_FAST_TAPS; table[6] = 0; table[7] = 0;
+    table[4] = (USDU_TAB_HEADER + 3 * size + 3) & ~3; table[5] = USDU_FAST_GROUP - 1 + USDU_FAST_TAPS; table[6] = USDU_PACKED_ROW; table[7] = 0;
     int32_t* bounds = table + USDU_TAB_HEADER;
     int32_t* kk = bounds + 2 * (int64_t)size;
-    int32_t* packed = kk + size;
+    int32_t* packed = table + table[4];
+    for (int32_t* q = kk + size; q < packed; ++q) *q = 0;
     for (int i = 0; i < size; ++i) {
         bounds[2 * i] = i; bounds[2 * i + 1] = 1; kk[i] = 1 << usdu::kPrecisionBits;
         int32_t* r = packed + (int64_t)i * USDU_PACKED_ROW;

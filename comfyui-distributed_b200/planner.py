@@ -143,6 +143,7 @@ class Plan:
     _tab_span: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
     _tab_packed: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_first: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
+    _tab_taps: Dict[Tuple[int, int], int] = field(default_factory=dict)
 
     # ---- construction ---------------------------------------------------------------
     @staticmethod
@@ -171,9 +172,11 @@ class Plan:
             self.tabs = tab if self.tabs is None else np.concatenate([self.tabs, tab])
             self._tab_off[key] = off
             self._tab_packed[key] = off + int(tab[4])          # pool index of packed row 0 (fast kernels)
+            taps = int(tab[6]) - 1 if tab[4] else int(tab[3])  # 7 or 15 staged taps per output on the fast path
+            self._tab_taps[key] = taps
             b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
             self._tab_first[key] = b[:, 0].astype(np.int64)
-            self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], 7)], 1)   # [lo, hi) per output (>= 7 taps staged)
+            self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], taps)], 1)   # [lo, hi) per output
         return self._tab_off[key]
 
     def _build_tables(self):
@@ -405,16 +408,18 @@ class Plan:
         x1, y1, ew, eh, pw, ph = geo.T
         ix0 = np.zeros(n, np.int64); ix1 = np.zeros(n, np.int64); iy0 = np.zeros(n, np.int64); iy1 = np.zeros(n, np.int64)
         rows_h = np.zeros(n, np.int64); rows_v = np.zeros(n, np.int64)
+        taps_h = np.zeros(n, np.int64); taps_v = np.zeros(n, np.int64)
         for key in {(int(a), int(b)) for a, b in zip(ew, pw)}:
             m = (ew == key[0]) & (pw == key[1])
             ix0[m] = self._first(key, ox0[m])
-            ix1[m] = np.minimum(self._first(key, ox0[m] + nat.FAST_BLOCK_W - 1) + nat.FAST_TAPS, key[0])
-            rows_h[m] = self._tab_packed[key]
+            ix1[m] = np.minimum(self._first(key, ox0[m] + nat.FAST_BLOCK_W - 1) + self._tab_taps[key], key[0])
+            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_taps[key]
         for key in {(int(a), int(b)) for a, b in zip(eh, ph)}:
             m = (eh == key[0]) & (ph == key[1])
             iy0[m] = self._first(key, oy0[m])
-            iy1[m] = np.minimum(self._first(key, oy0[m] + bh[m] - 1) + nat.FAST_TAPS, key[0])
-            rows_v[m] = self._tab_packed[key]
+            iy1[m] = np.minimum(self._first(key, oy0[m] + bh[m] - 1) + self._tab_taps[key], key[0])
+            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_taps[key]
+        J[:, nat.J_TAPS_H], J[:, nat.J_TAPS_V] = taps_h, taps_v
         px_abs = x1 + ix0
         lead = px_abs & 3
         J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_LEAD] = px_abs - lead, y1 + iy0, lead
@@ -490,18 +495,20 @@ class Plan:
         ox_base, oy_base = bx0 - x1, by0 - y1
         ix0 = np.zeros(n, np.int64); ix1 = np.zeros(n, np.int64); iy0 = np.zeros(n, np.int64); iy1 = np.zeros(n, np.int64)
         rows_h = np.zeros(n, np.int64); rows_v = np.zeros(n, np.int64)
+        taps_h = np.zeros(n, np.int64); taps_v = np.zeros(n, np.int64)
         for key in {(int(a), int(b)) for a, b in zip(pw, ew)}:
             m = (pw == key[0]) & (ew == key[1])
             ix0[m] = self._first(key, ox_base[m])
-            ix1[m] = np.minimum(self._first(key, ox_base[m] + bw - 1) + nat.FAST_TAPS, key[0])
-            rows_h[m] = self._tab_packed[key]
+            ix1[m] = np.minimum(self._first(key, ox_base[m] + bw - 1) + self._tab_taps[key], key[0])
+            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_taps[key]
         for key in {(int(a), int(b)) for a, b in zip(ph, eh)}:
             m = (ph == key[0]) & (eh == key[1])
             iy0[m] = self._first(key, oy_base[m])
-            iy1[m] = np.minimum(self._first(key, oy_base[m] + bh - 1) + nat.FAST_TAPS, key[0])
-            rows_v[m] = self._tab_packed[key]
+            iy1[m] = np.minimum(self._first(key, oy_base[m] + bh - 1) + self._tab_taps[key], key[0])
+            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_taps[key]
         lead = ix0 & 3
         J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
+        J[:, nat.J_TAPS_H], J[:, nat.J_TAPS_V] = taps_h, taps_v
         src = src_off + (iy0 * pw + ix0 - lead) * 3
         J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_LEAD] = src & 0xFFFFFFFF, src >> 32, lead
         J[:, nat.J_COLS], J[:, nat.J_ROWS], J[:, nat.J_IX0], J[:, nat.J_IY0] = ix1 - ix0, iy1 - iy0, ix0, iy0

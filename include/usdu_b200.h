@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 3
+#define USDU_ABI_VERSION 4
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -71,14 +71,16 @@ typedef enum usdu_status {
 /* Resample table at int32 offset o of the table pool:
  *   [o+0]=in_size [o+1]=out_size [o+2]=ksize [o+3]=max taps actually used by any output
  *   [o+4]=offset (from o) of the packed rows, 0 when the fast kernels cannot use this table
- *   [o+5]=max inputs read by USDU_FAST_GROUP consecutive outputs  [o+6],[o+7]=0
+ *   [o+5]=max inputs read by USDU_FAST_GROUP consecutive outputs
+ *   [o+6]=int32 per packed row: 8 (<= 7 taps) or 16 (<= 15 taps)  [o+7]=0
  *   [o+8 ...]            bounds: out_size x {first input index, tap count}
  *   [o+8+2*out_size ...] kk: out_size x ksize coefficients, 22-bit fixed point
- *   then packed rows: out_size x USDU_PACKED_ROW = {first input index, k0..k6}
+ *   then packed rows: out_size x [o+6] = {first input index, k0..k6} or {first, k0..k14}, zero padded
  * (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc.) */
 #define USDU_TAB_HEADER 8
 #define USDU_PACKED_ROW 8
-#define USDU_FAST_TAPS 7     /* taps per output handled by the fast kernels */
+#define USDU_FAST_TAPS 7     /* taps per output of the narrow fast path (packed rows of 8 int32) */
+#define USDU_FAST_TAPS_WIDE 15 /* ... and of the wide one (packed rows of 16 int32): scales up to ~2.3 */
 #define USDU_FAST_GROUP 8    /* consecutive outputs one thread computes from one register window */
 #define USDU_FAST_WINDOW 16  /* inputs held in that window */
 
@@ -132,6 +134,8 @@ typedef enum usdu_status {
 #define USDU_J_FRAME_LO 26 /* elements per frame PH*PW*3 */
 #define USDU_J_FRAME_HI 27
 #define USDU_J_NEXT 28     /* blend: index of the next record of the same block, -1 = last */
+#define USDU_J_TAPS_H 29   /* taps of the horizontal / vertical axis: USDU_FAST_TAPS or USDU_FAST_TAPS_WIDE */
+#define USDU_J_TAPS_V 30
 
 /* Feather-mask spec (host array, USDU_MASK_WORDS int32 each). */
 #define USDU_MASK_WORDS 16
@@ -160,7 +164,8 @@ int64_t usdu_resample_table_words(int in_size, int out_size);
 /* fill `table` (host, usdu_resample_table_words() int32) */
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table);
 /* table of an axis that keeps its size (size -> size): one tap of weight 2^22;
- * USDU_TAB_HEADER + size * (3 + USDU_PACKED_ROW) int32 */
+ * ((USDU_TAB_HEADER + 3*size + 3) & ~3) + size * USDU_PACKED_ROW int32.  Tables must start at a
+ * multiple of 4 int32 in the pool (their packed rows are read with 128-bit loads). */
 int usdu_build_identity_table(int size, int32_t* table);
 /* ImageFilter.GaussianBlur(radius) -> extended-box parameters (BoxBlur.c, 3 passes) */
 int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw);

@@ -50,7 +50,7 @@ def test_error_reporting_without_device_or_with_bad_args():
         nat.tile_blend(1, 1, 8, 8, 17, 1, 1, 1, 1, 1, 1, 8, 8, 0, 0, 0, 0)
 
 
-@pytest.mark.parametrize("n_in,n_out", [(576, 544), (544, 576), (320, 288), (288, 544), (100, 160), (1, 8), (2304, 1152), (37, 64)])
+@pytest.mark.parametrize("n_in,n_out", [(576, 544), (544, 576), (320, 288), (288, 544), (100, 160), (1, 8), (2304, 1152), (37, 64), (544, 64), (160, 100)])
 def test_resample_table_equals_oracle(n_in, n_out):
     tab = nat.build_resample_table(n_in, n_out)
     bounds, kk = orc.lanczos_coeffs(n_in, n_out)
@@ -60,17 +60,22 @@ def test_resample_table_equals_oracle(n_in, n_out):
     assert np.array_equal(tab[H:H + 2 * n_out].reshape(n_out, 2), bounds)
     assert np.array_equal(tab[H + 2 * n_out:H + 2 * n_out + n_out * ks].reshape(n_out, ks), kk)
     assert tab[3] == bounds[:, 1].max()
-    if tab[4]:                                           # packed rows: {first, k0..k6}, zero padded
-        rows = tab[tab[4]:tab[4] + 8 * n_out].reshape(n_out, 8)
+    assert tab[4] % 4 == 0 and tab.shape[0] % 4 == 0     # 128-bit loads of packed rows stay aligned in the pool
+    if tab[4]:                                           # packed rows: {first, k0..k(stride-2)}, zero padded
+        st = int(tab[6])
+        assert st == (8 if tab[3] <= 7 else 16) and tab[3] <= 15
+        rows = tab[tab[4]:tab[4] + st * n_out].reshape(n_out, st)
         assert np.array_equal(rows[:, 0], bounds[:, 0])
-        assert np.array_equal(rows[:, 1:], kk[:, :7] if ks >= 7 else np.pad(kk, ((0, 0), (0, 7 - ks))))
-        assert tab[3] <= 7 and tab[5] <= 16
+        kpad = kk[:, :st - 1] if ks >= st - 1 else np.pad(kk, ((0, 0), (0, st - 1 - ks)))
+        assert np.array_equal(rows[:, 1:], kpad)
+        assert not kk[:, st - 1:].any()                  # nothing was cut off
     else:
-        assert tab[3] > 7 or tab[5] > 16
+        assert tab[3] > 15
 
 
 def test_identity_table():
     tab = nat.build_identity_table(5)
+    assert tab[4] % 4 == 0 and tab.shape[0] % 4 == 0
     rows = tab[tab[4]:].reshape(5, 8)
     assert list(rows[:, 0]) == [0, 1, 2, 3, 4] and (rows[:, 1] == 1 << 22).all() and not rows[:, 2:].any()
 
