@@ -130,6 +130,56 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
     return res
 
 
+def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int, mask_blur: int,
+                  force_uniform_tiles: bool = True, group=None, stats: Optional[dict] = None) -> torch.Tensor:
+    """`semantics="exact"`: N ranks cooperatively execute the SINGLE-GPU
+    progressive job, so the result is bit-identical to process_single_gpu at any world size
+    (the reference's static mode is not -- SURVEY.md 8c).  Every rank keeps a full canvas;
+    the tiles of each dependency wave are split round-robin, each rank crops + samples its
+    share, one all-gather per wave exchanges the truncated u8 tiles, and every rank blends
+    the whole wave (replicated blend keeps all canvases identical).  Every rank returns the
+    result."""
+    from . import _native as nat
+    from .engine import Canvas, DevicePlan, _require_cuda, _stream_ptr, denoise_packed, _sorted_by_shape
+    from .planner import get_plan
+
+    _require_cuda(image, "image")
+    rank, world = dist_info(group)
+    B, H, W, _ = image.shape
+    plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
+    with torch.cuda.device(image.device):
+        dp = DevicePlan.get(plan, image.device)
+        canvas = Canvas(dp, B).load(image)
+        n_waves = 0
+        for wave in plan.waves():
+            wave = _sorted_by_shape(plan, wave)
+            shares = [wave[r::world] for r in range(world)]
+            mine = shares[rank]
+            where, sizes = tile_payload_layout(plan, shares, B)
+            payload = torch.zeros(max(sizes[rank], 16), dtype=torch.uint8, device=image.device)
+            if mine:
+                buf, offs = canvas.crop(mine)
+                out = denoise_packed(plan, mine, buf, offs, B, denoiser)
+                q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
+                nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
+                canvas.launches += 1
+                for i, tid in enumerate(mine):
+                    t = plan.tiles[tid]
+                    n = B * t.ph * t.pw * 3
+                    payload[where[tid][1]: where[tid][1] + n] = q[int(offs[i]): int(offs[i]) + n]
+            gathered, _ = all_gather_bytes(payload, group)
+            cap = gathered.shape[1]
+            offs_all = np.array([where[t][0] * cap + where[t][1] for t in wave], dtype=np.int64)
+            canvas.blend(wave, gathered.view(-1), offs_all)
+            n_waves += 1
+        res = canvas.result()
+    if stats is not None:
+        stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches
+        stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes
+        stats["tiles"], stats["waves"] = len(plan.tiles), n_waves
+    return res
+
+
 # --------------------------------------------------------------------------------------
 # collector
 # --------------------------------------------------------------------------------------

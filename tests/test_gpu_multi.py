@@ -72,6 +72,25 @@ def test_static_mode_matches_replay_oracle(world, case):
     _run(_w_static, world, case)
 
 
+def _w_exact(rank, world, case):
+    from comfyui_distributed_b200 import dist as udist
+    from comfyui_distributed_b200.denoise import T0Denoiser
+    kind, B, H, W, tile, pad, blur = case
+    img = make_input(kind, 21, B, H, W)
+    st = {}
+    out = udist.upscale_exact(torch.from_numpy(img).cuda(), T0Denoiser(9, 0.5), tile, tile, pad, blur, True, stats=st)
+    ref = orc.process_single(img, orc.make_t0_denoiser(9, 0.5), tile, tile, pad, blur, True)
+    assert np.array_equal(out.cpu().numpy(), ref)               # == the SINGLE-GPU result, on every rank
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case", CASES[:2], ids=lambda c: f"{c[0]}_{c[3]}x{c[2]}_b{c[1]}")
+def test_exact_mode_equals_single_gpu_oracle(world, case):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(_w_exact, world, case)
+
+
 def _w_all_ranks(rank, world):
     from comfyui_distributed_b200 import dist as udist, planner
     from comfyui_distributed_b200.denoise import T0Denoiser

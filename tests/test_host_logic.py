@@ -176,3 +176,16 @@ def test_mask_classes_and_worklists():
     assert bl.cover.shape[0] == sum(
         ((t.x1 + p.support(t)[2] - 1) // 64 - (t.x1 + p.support(t)[0]) // 64 + 1) *
         ((t.y1 + p.support(t)[3] - 1) // 32 - (t.y1 + p.support(t)[1]) // 32 + 1) for t in p.tiles)
+
+
+def test_image_batch_divider_matches_reference_chunking():
+    import torch
+    from comfyui_distributed_b200.nodes import NODE_CLASS_MAPPINGS
+    from comfyui_distributed_b200.nodes.utilities import chunk_bounds
+    node = NODE_CLASS_MAPPINGS["ImageBatchDivider"]()
+    assert chunk_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)] and chunk_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    x = torch.arange(7 * 2 * 2 * 3, dtype=torch.float32).reshape(7, 2, 2, 3)
+    outs = node.divide_batch(x, 3)
+    assert len(outs) == 10 and [o.shape[0] for o in outs] == [3, 2, 2] + [0] * 7
+    assert torch.equal(torch.cat(outs[:3]), x) and outs[0].data_ptr() == x.data_ptr()      # zero-copy views
+    assert [o.shape[0] for o in node.divide_batch(x, 99)] == [1, 1, 1, 1, 1, 1, 1, 0, 0, 0]
