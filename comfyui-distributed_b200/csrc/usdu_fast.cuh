@@ -68,6 +68,8 @@ __device__ __forceinline__ void dot4(const uint32_t (&w)[TAPS], const PackedRow<
     for (int r = 0; r < R; ++r) acc[r] = 1 << (kPrecisionBits - 1);
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
+        // (moving one of the four extractions to the integer-FMA pipe with IMAD.HI -- hi32(w*2^8)
+        // == w >> 24 -- was measured and is slower: crop +4 %, blend +6 %)
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] += (int)__byte_perm(w[t], 0, 0x4440 + r) * row.k[t];
     }
