@@ -30,17 +30,20 @@ def dist_info(group=None) -> Tuple[int, int]:
 # --------------------------------------------------------------------------------------
 # transport (device agnostic: NCCL on CUDA tensors, gloo on CPU tensors in the tests)
 # --------------------------------------------------------------------------------------
-def all_gather_bytes(payload: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int]]:
+def all_gather_bytes(payload: torch.Tensor, group=None, sizes: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, List[int]]:
     """All-gather variable-length u8 payloads.  Returns (buffer [world, cap], sizes).
-    One size exchange (int64 all_gather) + one padded all_gather_into_tensor."""
+    One padded all_gather_into_tensor, preceded by a size exchange (int64 all_gather) only
+    when the caller cannot supply `sizes` (the tile paths know them from the plan)."""
     assert payload.dtype == torch.uint8 and payload.dim() == 1
     rank, world = dist_info(group)
     if world == 1:
         return payload.view(1, -1), [payload.numel()]
-    n = torch.tensor([payload.numel()], dtype=torch.int64, device=payload.device)
-    sizes = torch.empty(world, dtype=torch.int64, device=payload.device)
-    td.all_gather_into_tensor(sizes, n, group=group)
-    sizes = [int(s) for s in sizes.tolist()]
+    if sizes is None:
+        n = torch.tensor([payload.numel()], dtype=torch.int64, device=payload.device)
+        got = torch.empty(world, dtype=torch.int64, device=payload.device)
+        td.all_gather_into_tensor(got, n, group=group)
+        sizes = got.tolist()
+    sizes = [int(s) for s in sizes]
     cap = max(max(sizes), 1)
     cap = (cap + 15) // 16 * 16
     send = payload
@@ -97,17 +100,26 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         raise ValueError(f"assignment has {len(asg)} participants, world size is {world}")
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
-        canvas = Canvas(dp, B).load(image)
-        base = canvas.clone() if (all_ranks_result and rank != 0) else None
-        shipped = run_progressive(canvas, asg[rank], denoiser, keep_processed=world > 1)
+        from . import engine as _eng
+        # payload layout follows every rank's processing order (wave by wave), so a wave's
+        # packed u8 tiles land in one contiguous span
+        proc = [_eng.processing_order(plan, a) for a in asg]
+        where, sizes = tile_payload_layout(plan, proc, B)
+        sizes = [max(sz, 16) for sz in sizes]
+        graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
+        payload = None
+        if graphed:      # this rank's wave loop (crop -> sampler -> local blend -> u8 pack) as one CUDA graph
+            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank],
+                                       payload_bytes=sizes[rank] if world > 1 else 0, where=where)
+            canvas, payload, base = gw.replay(image), gw.payload, None
+        else:
+            canvas = Canvas(dp, B).load(image)
+            base = canvas.clone() if (all_ranks_result and rank != 0) else None
+            if world > 1:
+                payload = torch.zeros(sizes[rank], dtype=torch.uint8, device=image.device)
+            run_progressive(canvas, asg[rank], denoiser, payload=payload, where=where)
         if world > 1:
-            where, sizes = tile_payload_layout(plan, asg, B)
-            payload = torch.zeros(sizes[rank], dtype=torch.uint8, device=image.device)
-            for tid in asg[rank]:
-                off = where[tid][1]
-                t = shipped[tid]
-                payload[off: off + t.numel()] = t.reshape(-1)
-            gathered, _ = all_gather_bytes(payload, group)
+            gathered, _ = all_gather_bytes(payload, group, sizes=sizes)
             cap = gathered.shape[1]
             if rank == 0 or all_ranks_result:
                 target = canvas

@@ -257,11 +257,19 @@ def _sorted_by_shape(plan: Plan, ids: Sequence[int]) -> List[int]:
     return sorted(ids, key=lambda i: (plan.tiles[i].ph, plan.tiles[i].pw, i))
 
 
-def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, keep_processed: bool = False):
+def processing_order(plan: Plan, tile_ids: Sequence[int]) -> List[int]:
+    """The order in which run_progressive handles `tile_ids`: wave by wave, same-shape tiles
+    adjacent inside a wave (every rank can compute every other rank's order from the plan)."""
+    return [t for w in plan.waves(tile_ids) for t in _sorted_by_shape(plan, w)]
+
+
+def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, keep_processed: bool = False,
+                    payload: Optional[torch.Tensor] = None, where: Optional[dict] = None):
     """Process `order` (tile ids) with the reference's progressive semantics on `canvas`
     (single_gpu.py:40-64 / static.py:242-280): wave by wave, each wave = crop kernel,
-    one sampler call, blend kernel.  Returns {tile id: u8 processed tile [B,ph,pw,3]}
-    when keep_processed (what a static-mode worker ships to the master)."""
+    one sampler call, blend kernel.  What a static-mode worker ships to the master (the
+    truncated u8 tiles, worker_comms.py:30-33) is either returned as {tile id: u8 [B,ph,pw,3]}
+    (keep_processed) or written straight into `payload` at `where[tile] = (rank, byte offset)`."""
     plan, B = canvas.plan, canvas.B
     shipped: Dict[int, torch.Tensor] = {}
     for wave in plan.waves(order):
@@ -269,7 +277,20 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
         buf, offs = canvas.crop(wave)
         out = denoise_packed(plan, wave, buf, offs, B, denoiser)
         canvas.blend(wave, out, offs)
-        if keep_processed:
+        if payload is not None:
+            sizes = [B * plan.tiles[t].ph * plan.tiles[t].pw * 3 for t in wave]
+            base = where[wave[0]][1]
+            dense = all(sz % 16 == 0 for sz in sizes) and all(where[t][1] == base + int(offs[i]) for i, t in enumerate(wave))
+            if dense:        # the wave occupies one contiguous span of the payload: pack in place
+                nat.pack_tiles_u8(out.data_ptr(), payload[base:].data_ptr(), out.numel(), _stream_ptr())
+                canvas.launches += 1
+            else:
+                q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
+                nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
+                canvas.launches += 1
+                for i, tid in enumerate(wave):
+                    payload[where[tid][1]: where[tid][1] + sizes[i]] = q[int(offs[i]): int(offs[i]) + sizes[i]]
+        elif keep_processed:
             q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
             nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
             canvas.launches += 1
@@ -288,18 +309,22 @@ class GraphedWaves:
 
     _cache: Dict[tuple, "GraphedWaves"] = {}
 
-    def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile]):
+    def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
+                 order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
+                 where: Optional[dict] = None):
         global PROFILE
         self.canvas = Canvas(dp, B)
         self.denoiser = denoiser
-        order = range(len(dp.plan.tiles))
+        order = list(range(len(dp.plan.tiles))) if order is None else list(order)
+        self.shipped: Dict[int, torch.Tensor] = {}
+        self.payload = (torch.zeros(payload_bytes, dtype=torch.uint8, device=dp.device) if payload_bytes else None)
         self.canvas.buf.zero_()
         side = torch.cuda.Stream(device=dp.device)
         side.wait_stream(torch.cuda.current_stream(dp.device))
         saved = PROFILE
         PROFILE = None
         with torch.cuda.stream(side):                 # warm-up: fills every cache (work lists, noise)
-            run_progressive(self.canvas, order, denoiser)
+            run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where)
         torch.cuda.current_stream(dp.device).wait_stream(side)
         torch.cuda.synchronize(dp.device)
         self.canvas.launches = 0
@@ -310,7 +335,7 @@ class GraphedWaves:
             profile.capturing = True
         try:
             with torch.cuda.graph(self.graph):
-                run_progressive(self.canvas, order, denoiser)
+                self.shipped = run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where)
         finally:
             PROFILE = saved
             if profile is not None:
@@ -319,14 +344,25 @@ class GraphedWaves:
         self.bytes_per_replay = self.canvas.algo_bytes
 
     @classmethod
-    def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None) -> "GraphedWaves":
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC)
+    def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None,
+            order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
+            where: Optional[dict] = None) -> "GraphedWaves":
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC,
+               None if order is None else tuple(order), keep_processed, payload_bytes)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
             if len(cls._cache) > 4:
                 cls._cache.clear()
-            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile)
+            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload_bytes, where)
         return gw
+
+    def replay(self, image: torch.Tensor) -> Canvas:
+        """Q0 from the caller's tensor (eager), then the captured wave loop."""
+        c = self.canvas
+        c.launches, c.algo_bytes = self.launches_per_replay, self.bytes_per_replay
+        c.load(image)
+        self.graph.replay()
+        return c
 
 
 def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
@@ -342,12 +378,7 @@ def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, til
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
         if use_graph:
-            gw = GraphedWaves.get(dp, B, denoiser, PROFILE)
-            canvas = gw.canvas
-            canvas.launches, canvas.algo_bytes = gw.launches_per_replay, gw.bytes_per_replay
-            canvas.flags = nat.FLAG_FAST if (plan.fast and not FORCE_GENERIC) else 0
-            canvas.load(image)                        # Q0, eager, straight from the caller's tensor
-            gw.graph.replay()
+            canvas = GraphedWaves.get(dp, B, denoiser, PROFILE).replay(image)
         else:
             canvas = Canvas(dp, B).load(image)
             run_progressive(canvas, range(len(plan.tiles)), denoiser)
