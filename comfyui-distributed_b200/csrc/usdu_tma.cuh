@@ -108,6 +108,9 @@ __device__ __forceinline__ void store_3d(const CUtensorMap* map, int x, int y, i
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// enough before a CTA exits: the bulk store has finished READING shared memory (the global writes
+// complete by the end of the grid like any other store)
+__device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace tma
 }  // namespace usdu

@@ -264,7 +264,7 @@ def processing_order(plan: Plan, tile_ids: Sequence[int]) -> List[int]:
 
 
 def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, keep_processed: bool = False,
-                    payload: Optional[torch.Tensor] = None, where: Optional[dict] = None):
+                    payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()):
     """Process `order` (tile ids) with the reference's progressive semantics on `canvas`
     (single_gpu.py:40-64 / static.py:242-280): wave by wave, each wave = crop kernel,
     one sampler call, blend kernel.  What a static-mode worker ships to the master (the
@@ -272,11 +272,19 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     (keep_processed) or written straight into `payload` at `where[tile] = (rank, byte offset)`."""
     plan, B = canvas.plan, canvas.B
     shipped: Dict[int, torch.Tensor] = {}
+    scratch = None
     for wave in plan.waves(order):
         wave = _sorted_by_shape(plan, wave)
-        buf, offs = canvas.crop(wave)
+        if "crop" in skip:      # bench.py's differencing measurement: same graph minus one kernel kind
+            offs, total = plan.slot_offsets(wave, B)
+            if scratch is None or scratch.numel() < total:
+                scratch = torch.zeros(total, dtype=torch.float32, device=canvas.buf.device)
+            buf = scratch[:total]
+        else:
+            buf, offs = canvas.crop(wave)
         out = denoise_packed(plan, wave, buf, offs, B, denoiser)
-        canvas.blend(wave, out, offs)
+        if "blend" not in skip:
+            canvas.blend(wave, out, offs)
         if payload is not None:
             sizes = [B * plan.tiles[t].ph * plan.tiles[t].pw * 3 for t in wave]
             base = where[wave[0]][1]
@@ -311,7 +319,7 @@ class GraphedWaves:
 
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
                  order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
-                 where: Optional[dict] = None):
+                 where: Optional[dict] = None, skip: Sequence[str] = ()):
         global PROFILE
         self.canvas = Canvas(dp, B)
         self.denoiser = denoiser
@@ -324,7 +332,7 @@ class GraphedWaves:
         saved = PROFILE
         PROFILE = None
         with torch.cuda.stream(side):                 # warm-up: fills every cache (work lists, noise)
-            run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where)
+            run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
         torch.cuda.current_stream(dp.device).wait_stream(side)
         torch.cuda.synchronize(dp.device)
         self.canvas.launches = 0
@@ -335,7 +343,7 @@ class GraphedWaves:
             profile.capturing = True
         try:
             with torch.cuda.graph(self.graph):
-                self.shipped = run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where)
+                self.shipped = run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
         finally:
             PROFILE = saved
             if profile is not None:
@@ -346,14 +354,14 @@ class GraphedWaves:
     @classmethod
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None,
             order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
-            where: Optional[dict] = None) -> "GraphedWaves":
+            where: Optional[dict] = None, skip: Sequence[str] = ()) -> "GraphedWaves":
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC,
-               None if order is None else tuple(order), keep_processed, payload_bytes)
+               None if order is None else tuple(order), keep_processed, payload_bytes, tuple(skip))
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
-            if len(cls._cache) > 4:
+            if len(cls._cache) > 6:
                 cls._cache.clear()
-            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload_bytes, where)
+            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload_bytes, where, skip)
         return gw
 
     def replay(self, image: torch.Tensor) -> Canvas:
@@ -367,7 +375,7 @@ class GraphedWaves:
 
 def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
                    mask_blur: int, force_uniform_tiles: bool = True, stats: Optional[dict] = None,
-                   use_graph: Optional[bool] = None) -> torch.Tensor:
+                   use_graph: Optional[bool] = None, _skip: Sequence[str] = ()) -> torch.Tensor:
     """One-GPU job on a CUDA image [B,H,W,3] fp32 -> fp32 (values k/255), exact
     progressive semantics of process_single_gpu."""
     _require_cuda(image, "image")
@@ -378,7 +386,7 @@ def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, til
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
         if use_graph:
-            canvas = GraphedWaves.get(dp, B, denoiser, PROFILE).replay(image)
+            canvas = GraphedWaves.get(dp, B, denoiser, PROFILE, skip=_skip).replay(image)
         else:
             canvas = Canvas(dp, B).load(image)
             run_progressive(canvas, range(len(plan.tiles)), denoiser)
