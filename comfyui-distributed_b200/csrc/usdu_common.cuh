@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/usdu_b200.h"
 
@@ -62,6 +63,29 @@ __device__ __forceinline__ uint32_t composite8(uint32_t S, uint32_t D, uint32_t 
     uint32_t tmp = S * (A * 128u) + D * ((255u - A) * 128u) + (0x80u << 7);
     tmp = ((tmp >> 8) + tmp) >> 8;
     return tmp >> 7;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of the wave loop reads only STATIC data (job records, tables) in its prologue.
+// pdl_launch_dependents() lets the next kernel of the stream start being scheduled while this
+// one is still running; pdl_wait() (griddepcontrol.wait) blocks until the previous kernel has
+// completed and flushed, and must precede the first access to data that kernel produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch with the programmatic-stream-serialization attribute (captured as a programmatic edge
+// inside CUDA graphs).  USDU_NO_PDL=1 in the environment falls back to plain launches.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static int use = -1;
+    if (use < 0) { const char* e = getenv("USDU_NO_PDL"); use = (e && e[0] == '1') ? 0 : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 struct TableView {

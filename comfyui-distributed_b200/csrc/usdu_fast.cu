@@ -213,12 +213,16 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
     float* lut = reinterpret_cast<float*>(smem + region + kHeadBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + region + kHeadBytes + 1024);
     uint32_t* in = reinterpret_cast<uint32_t*>(smem + region + kHeadBytes + 1024 + 16);
+    pdl_launch_dependents();
     load_job(job_sm, jobs, blockIdx.x);
     if (kTma && threadIdx.x == 0) tma::mbar_init(bar, 1);
+    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
     __syncthreads();
     const JobView J{job_sm};
     const int b = blockIdx.y;
     const int xw = plane_words(patch_w);
+    stage_rows_v(rows_v, tabs, J);
+    pdl_wait();                                // the canvas is the previous kernel's output
     if (kTma && threadIdx.x == 0) {
         const int x = (J[USDU_J_SRC_A] * 3) & ~15, y = J[USDU_J_SRC_B];           // 16-byte aligned box start
         // second box only when the patch needs it and it starts inside the canvas row
@@ -227,8 +231,6 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
         tma::load_3d(raw, &cmap, x, y, b, bar);
         if (two) tma::load_3d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, b, bar);
     }
-    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
-    stage_rows_v(rows_v, tabs, J);
     stage_and_hpass(tabs, J, in, mid, xw, [&]() {
         if (kTma) {
             tma::mbar_wait(bar, 0);
@@ -336,9 +338,12 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
     const JobView J{job_sm};
     DTile D{smem, block_rows};
     int idx = blockIdx.x;
+    pdl_launch_dependents();
     load_job(job_sm, jobs, idx);
     if (threadIdx.x == 0) tma::mbar_init(bar, 1);
     __syncthreads();
+    stage_rows_v(rows_v, tabs, J);
+    pdl_wait();                                // canvas and processed tiles come from earlier kernels
     const int bx3 = J[USDU_J_DST_X] * 3, by = J[USDU_J_DST_Y];
     const bool two = bx3 + kDBox < W3;         // the right half exists (a box may not START past the row end)
     if (threadIdx.x == 0) {                    // canvas block -> shared, asynchronously
@@ -352,8 +357,8 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
             __syncthreads();                   // the previous tile's passes are done with job / rows / in / mid
             load_job(job_sm, jobs, idx);
             __syncthreads();
+            stage_rows_v(rows_v, tabs, J);
         }
-        stage_rows_v(rows_v, tabs, J);
         const int64_t first_el = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
         if (dbg & 2) {       // timing experiment: no H pass
             if (!(dbg & 1)) stage_f32(in, xw, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
@@ -424,9 +429,9 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (use_tma)
-        crop_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap);
+        USDU_CUDA(launch_pdl(crop_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap));
     else
-        crop_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap);
+        USDU_CUDA(launch_pdl(crop_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, patch_h, W * 3, cmap));
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
@@ -452,9 +457,9 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (src_is_u8)
-        blend_fast_kernel<true><<<dim3(n_items, B), kT, smem, st>>>(tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap);
+        USDU_CUDA(launch_pdl(blend_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap));
     else
-        blend_fast_kernel<false><<<dim3(n_items, B), kT, smem, st>>>(tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap);
+        USDU_CUDA(launch_pdl(blend_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap));
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

@@ -121,6 +121,8 @@ unpack_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int6
 __global__ void __launch_bounds__(kThreads)
 t0_denoise_kernel(const float4* __restrict__ x, const float4* __restrict__ nd, float4* __restrict__ out,
                   int64_t n4, int64_t frame4, float omd) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 a = __ldcs(x + i);
         const float4 b = __ldg(nd + (i % frame4));
@@ -503,9 +505,9 @@ int usdu_t0_denoise(const float* tiles_dev, const float* noise_scaled_dev, float
     USDU_REQUIRE(n % 4 == 0 && frame % 4 == 0 && n % frame == 0, "usdu_t0_denoise: n and frame must be multiples of 4, n of frame");
     USDU_REQUIRE((((uintptr_t)tiles_dev | (uintptr_t)noise_scaled_dev | (uintptr_t)out_dev) & 15) == 0, "usdu_t0_denoise: pointers must be 16-byte aligned");
     const int grid = grid_for((n / 4 + kThreads - 1) / kThreads);
-    t0_denoise_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(tiles_dev), reinterpret_cast<const float4*>(noise_scaled_dev),
-        reinterpret_cast<float4*>(out_dev), n / 4, frame / 4, one_minus_d);
+    USDU_CUDA(launch_pdl(t0_denoise_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream,
+                         reinterpret_cast<const float4*>(tiles_dev), reinterpret_cast<const float4*>(noise_scaled_dev),
+                         reinterpret_cast<float4*>(out_dev), n / 4, frame / 4, one_minus_d));
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
