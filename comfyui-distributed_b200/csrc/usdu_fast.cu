@@ -235,7 +235,7 @@ crop_fast_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const
         if (kTma) {
             tma::mbar_wait(bar, 0);
             stage_from_raw(in, xw, raw, J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD], (J[USDU_J_SRC_A] * 3) & 15);
-            __syncthreads();               // raw (aliased with mid) is consumed before the H pass overwrites it
+            // raw is aliased with mid: stage_and_hpass() synchronises before the H pass overwrites it
         } else {
             const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + (int64_t)J[USDU_J_SRC_A] * 3;
             stage_u8(in, xw, src, pitch, J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);

@@ -351,13 +351,26 @@ class Plan:
         ends = np.minimum(starts + block, n_out) - 1
         return int((sp[ends, 1] - sp[starts, 0]).max())
 
-    def block_shape(self, use_fast: bool, n_tile_frames: int = 1 << 30) -> Tuple[int, int]:
-        """Block edge of a launch.  Small launches (few tiles) are latency bound: shorter
-        blocks give the 148 SMs more CTAs to overlap (at the price of more halo rows)."""
+    SLOTS = 148 * 4            # resident CTAs of the fast kernels on a B200 (4 per SM)
+
+    def block_shape(self, use_fast: bool, extents: Optional[Sequence[Tuple[int, int]]] = None, frames: int = 1) -> Tuple[int, int]:
+        """Block edge of a launch.  `extents` = (width, height) in pixels each tile covers in
+        the launch's block space.  The block height is chosen by a simple wave model:
+        cost(bh) = ceil(#CTAs / resident slots) * (bh + halo/fixed rows) -- short blocks give
+        small (latency bound) launches more CTAs, and large launches avoid a nearly empty
+        last wave."""
         if not use_fast:
             return nat.BLOCK_W, nat.BLOCK_H
-        bh = nat.FAST_BLOCK_H if n_tile_frames >= 5 else (16 if n_tile_frames >= 3 else 8)
-        return nat.FAST_BLOCK_W, bh
+        bw = nat.FAST_BLOCK_W
+        if not extents:
+            return bw, nat.FAST_BLOCK_H
+        best = None
+        for bh in (8, 12, 16, 20, 24, 28, 32):
+            n = sum(((w + bw - 1) // bw + 1) * ((h + bh - 1) // bh + 1) for w, h in extents) * frames   # +1: unaligned windows
+            cost = math.ceil(n / self.SLOTS) * (bh + 12)
+            if best is None or cost < best[0] or (cost == best[0] and bh > best[1]):
+                best = (cost, bh)
+        return bw, best[1]
 
     def _crop_block_rows(self, t: Tile, use_fast: bool, bh_max: int) -> int:
         """Output rows per crop block (fast path: keep the staged input rows <= 40)."""
@@ -374,7 +387,7 @@ class Plan:
         rows = []
         pw_max = ph_max = 1
         nbytes = 0
-        bw, bh_max = self.block_shape(use_fast, len(tile_ids) * B)
+        bw, bh_max = self.block_shape(use_fast, [(self.tiles[t].pw - nat.FAST_BLOCK_W, self.tiles[t].ph) for t in tile_ids], B)
         for i, tid in enumerate(tile_ids):
             t = self.tiles[tid]
             bh = self._crop_block_rows(t, use_fast, bh_max)
@@ -441,7 +454,11 @@ class Plan:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
         given order (the order of `tile_ids` IS the blend order)."""
         use_fast = self.fast if use_fast is None else (use_fast and self.fast)
-        bw, bh = self.block_shape(use_fast, len(tile_ids) * B)
+        ext = []
+        for t in tile_ids:
+            sx0, sy0, sx1, sy1 = self.support(self.tiles[t])
+            ext.append((sx1 - sx0, sy1 - sy0))
+        bw, bh = self.block_shape(use_fast, ext, B)
         nbx = (self.W + bw - 1) // bw
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1

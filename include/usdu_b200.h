@@ -81,8 +81,7 @@ typedef enum usdu_status {
 #define USDU_PACKED_ROW 8
 #define USDU_FAST_TAPS 7     /* taps per output of the narrow fast path (packed rows of 8 int32) */
 #define USDU_FAST_TAPS_WIDE 15 /* ... and of the wide one (packed rows of 16 int32): scales up to ~2.3 */
-#define USDU_FAST_GROUP 8    /* consecutive outputs one thread computes from one register window */
-#define USDU_FAST_WINDOW 16  /* inputs held in that window */
+#define USDU_FAST_GROUP 8    /* table word 5 = inputs read by this many consecutive outputs (diagnostic) */
 
 /* Crop work item: one block of one tile's processing-size output. */
 #define USDU_CROP_ITEM_WORDS 6
