@@ -201,7 +201,7 @@ __device__ __forceinline__ uint32_t vpass_at(const uint8_t* mid, int mid_pitch, 
 __global__ void __launch_bounds__(kThreads)
 crop_resize_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pitch,
                    const int32_t* __restrict__ tiles, const int32_t* __restrict__ tabs,
-                   const int32_t* __restrict__ items, float* __restrict__ out, int in_pitch, int max_rows) {
+                   const int32_t* __restrict__ items, float* __restrict__ out, int in_pitch, int max_rows, int blk_w, int blk_h) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int32_t* it = items + (int64_t)blockIdx.x * USDU_CROP_ITEM_WORDS;
     const int32_t* T = tiles + (int64_t)it[0] * USDU_TILE_WORDS;
@@ -211,7 +211,7 @@ crop_resize_kernel(const uint8_t* __restrict__ canvas, int H, int W, int64_t pit
     const int x1 = T[USDU_T_X1], y1 = T[USDU_T_Y1];
     const int pw = T[USDU_T_PW], ph = T[USDU_T_PH];
     const int tabH = T[USDU_T_TAB_CROP_H], tabV = T[USDU_T_TAB_CROP_V];
-    const int ow = min(BW, pw - ox0), oh = min(BH, ph - oy0);
+    const int ow = min(blk_w, pw - ox0), oh = min(blk_h, ph - oy0);
     int ix0, ix1, iy0, iy1;
     axis_range(tabs, tabH, ox0, ow, ix0, ix1);
     axis_range(tabs, tabV, oy0, oh, iy0, iy1);
@@ -253,12 +253,12 @@ __global__ void __launch_bounds__(kThreads)
 blend_kernel(uint8_t* __restrict__ canvas, int H, int W, int64_t pitch, const int32_t* __restrict__ tiles,
              const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
              const int32_t* __restrict__ items, const int32_t* __restrict__ cover,
-             const void* __restrict__ src_v, int in_pitch, int max_rows) {
+             const void* __restrict__ src_v, int in_pitch, int max_rows, int blk_w, int blk_h) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int32_t* it = items + (int64_t)blockIdx.x * USDU_BLEND_ITEM_WORDS;
     const int b = blockIdx.y;
     const int bx0 = it[0], by0 = it[1];
-    const int bw = min(BW, W - bx0), bh = min(BH, H - by0);
+    const int bw = min(blk_w, W - bx0), bh = min(blk_h, H - by0);
     const int d_pitch = BW * 3;
     uint8_t* D = smem;                              // [BH][BW*3] canvas block
     uint8_t* mid = D + BH * d_pitch;                // [max_rows][BW*3]
@@ -598,8 +598,11 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
     const size_t smem = (size_t)patch_h * in_pitch + (size_t)patch_h * BW * 3;
     int s = smem_optin((const void*)crop_resize_kernel, smem);
     if (s != USDU_OK) return s;
+    int blk_h = (flags >> 8) & 0xFF, blk_w = (flags >> 16) & 0xFF;     // generic path: optional smaller blocks
+    if (blk_h <= 0 || blk_h > BH) blk_h = BH;
+    if (blk_w <= 0 || blk_w > BW) blk_w = BW;
     crop_resize_kernel<<<dim3(n_items, B), kThreads, smem, (cudaStream_t)stream>>>(
-        canvas_dev, H, W, pitch, tiles_dev, tabs_dev, items_dev, out_dev, in_pitch, patch_h);
+        canvas_dev, H, W, pitch, tiles_dev, tabs_dev, items_dev, out_dev, in_pitch, patch_h, blk_w, blk_h);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
@@ -626,12 +629,15 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, con
     const void* fn = src_is_u8 ? (const void*)blend_kernel<true> : (const void*)blend_kernel<false>;
     int s = smem_optin(fn, smem);
     if (s != USDU_OK) return s;
+    int blk_h = (flags >> 8) & 0xFF, blk_w = (flags >> 16) & 0xFF;     // generic path: optional smaller blocks
+    if (blk_h <= 0 || blk_h > BH) blk_h = BH;
+    if (blk_w <= 0 || blk_w > BW) blk_w = BW;
     if (src_is_u8)
         blend_kernel<true><<<dim3(n_items, B), kThreads, smem, (cudaStream_t)stream>>>(
-            canvas_dev, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, cover_dev, src_dev, in_pitch, patch_h);
+            canvas_dev, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, cover_dev, src_dev, in_pitch, patch_h, blk_w, blk_h);
     else
         blend_kernel<false><<<dim3(n_items, B), kThreads, smem, (cudaStream_t)stream>>>(
-            canvas_dev, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, cover_dev, src_dev, in_pitch, patch_h);
+            canvas_dev, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, cover_dev, src_dev, in_pitch, patch_h, blk_w, blk_h);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

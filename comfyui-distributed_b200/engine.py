@@ -182,8 +182,8 @@ class Canvas:
         _launch("crop_resize", wl.algo_bytes * self.B,
                 lambda: nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch,
                                              self.dp.tiles.data_ptr(), self.dp.tabs.data_ptr(), items.data_ptr(),
-                                             items.shape[0], wl.patch_w, wl.patch_h, out.data_ptr(), self.flags,
-                                             _stream_ptr()))
+                                             items.shape[0], wl.patch_w, wl.patch_h, out.data_ptr(),
+                                             self.flags | (wl.block_rows << 8) | (wl.block_cols << 16), _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
         return out, offs
@@ -203,7 +203,7 @@ class Canvas:
         p = self.plan
         src = src.contiguous()
         n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
-        flags = self.flags | (wl.block_rows << 8)
+        flags = self.flags | (wl.block_rows << 8) | (wl.block_cols << 16)
         cover_ptr = cover.data_ptr() if cover is not None else 0
         _launch("blend", wl.algo_bytes * self.B,
                 lambda: nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),

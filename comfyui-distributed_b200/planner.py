@@ -117,7 +117,8 @@ class WorkList:
     patch_h: int
     algo_bytes: int                   # algorithmic HBM bytes of the launch per frame
     n_launch: int = -1                # grid size when it differs from len(items) (chained fast jobs)
-    block_rows: int = 0               # canvas block height of a fast blend launch
+    block_rows: int = 0               # block height the work list was built for (passed in `flags`)
+    block_cols: int = 0               # block width (generic kernels only)
 
 
 @dataclass
@@ -144,6 +145,7 @@ class Plan:
     _tab_packed: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_first: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
     _tab_taps: Dict[Tuple[int, int], int] = field(default_factory=dict)
+    _gblock: Optional[Tuple[int, int]] = None
 
     # ---- construction ---------------------------------------------------------------
     @staticmethod
@@ -360,7 +362,7 @@ class Plan:
         small (latency bound) launches more CTAs, and large launches avoid a nearly empty
         last wave."""
         if not use_fast:
-            return nat.BLOCK_W, nat.BLOCK_H
+            return self._generic_block
         bw = nat.FAST_BLOCK_W
         if not extents:
             return bw, nat.FAST_BLOCK_H
@@ -372,10 +374,29 @@ class Plan:
                 best = (cost, bh)
         return bw, best[1]
 
+    @property
+    def _generic_block(self) -> Tuple[int, int]:
+        """Block of the generic kernels: 64 x 32 unless an extreme scale (a canvas much smaller
+        than a tile) makes the input patch of such a block exceed shared memory; then halve."""
+        if self._gblock is None:
+            bw, bh = nat.BLOCK_W, nat.BLOCK_H
+            while True:
+                pw_ = max([self._span_max(a, b, bw, False) for (a, b) in self._tab_span] or [bw])
+                ph_ = max([self._span_max(a, b, bh, False) for (a, b) in self._tab_span] or [bh])
+                smem = nat.BLOCK_H * nat.BLOCK_W * 3 + ph_ * nat.BLOCK_W * 3 + ph_ * ((pw_ * 3 + 15) // 16 * 16)
+                if smem <= 200 * 1024 or (bw <= 4 and bh <= 4):
+                    break
+                if pw_ * bh >= ph_ * bw and bw > 4 or bh <= 4:
+                    bw //= 2
+                else:
+                    bh //= 2
+            self._gblock = (bw, bh)
+        return self._gblock
+
     def _crop_block_rows(self, t: Tile, use_fast: bool, bh_max: int) -> int:
         """Output rows per crop block (fast path: keep the staged input rows <= 40)."""
         if not use_fast:
-            return nat.BLOCK_H
+            return self._generic_block[1]
         for bh in range(bh_max, 7, -1):
             if self._span_max(t.eh, t.ph, bh, True) <= 40:
                 return bh
@@ -406,7 +427,8 @@ class Plan:
         if use_fast and items.shape[0]:
             items = self._crop_jobs(items)
         items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
-        return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes), offs, total
+        return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes,
+                        block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw), offs, total
 
     def _first(self, key: Tuple[int, int], idx: np.ndarray) -> np.ndarray:
         f = self._tab_first[key]
@@ -498,7 +520,8 @@ class Plan:
         o = np.asarray(offs, dtype=np.int64)[seq]
         cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32
         return WorkList(np.ascontiguousarray(items.astype(np.uint32).view(np.int32)),
-                        np.ascontiguousarray(cover.astype(np.uint32).view(np.int32)), pw_max, ph_max, nbytes)
+                        np.ascontiguousarray(cover.astype(np.uint32).view(np.int32)), pw_max, ph_max, nbytes,
+                        block_rows=bh, block_cols=bw)
 
 
     def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh) -> np.ndarray:

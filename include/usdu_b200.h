@@ -178,6 +178,10 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
 /* usdu_tile_blend with USDU_FLAG_FAST: bits 8..15 of `flags` carry the canvas block height the
  * job records were built for (1..USDU_FAST_BLOCK_H); the canvas block travels by TMA. */
 #define USDU_FLAG_BLOCK_ROWS(n) ((n) << 8)
+/* generic kernels (no USDU_FLAG_FAST): optional block size the work items were built for, rows in
+ * bits 8..15 (<= USDU_BLOCK_H), columns in bits 16..23 (<= USDU_BLOCK_W); 0 = the default block.
+ * The planner shrinks blocks when an extreme down-scale would not fit shared memory. */
+#define USDU_FLAG_BLOCK_COLS(n) ((n) << 16)
 /* Q0: canvas_u8[b][y][x*3+c] = (uint8)(255.f * img[b][y][x][c])   (utils/image.py:8-10)
  * pitch = bytes per canvas row (>= 3*W, multiple of 16); frame stride = H*pitch. */
 int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W,
