@@ -18,7 +18,7 @@ import torch
 
 from .. import dist as usdu_dist
 from ..denoise import ComfySampler
-from ..engine import upscale_single
+from ..engine import upscale_host, upscale_single
 
 try:  # ComfyUI supplies these lists; outside ComfyUI keep the signature importable
     import comfy.samplers as _cs
@@ -106,6 +106,14 @@ class UltimateSDUpscaleDistributed:
 
         src_device = upscaled_image.device
         dev = src_device if upscaled_image.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        self.last_stats = {}
+        if not upscaled_image.is_cuda and not distributed:
+            # ComfyUI IMAGE tensors live on the host: upload, kernels and download overlap band by band
+            _, H, W, _ = upscaled_image.shape
+            denoiser = self._make_denoiser(model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler,
+                                           denoise, tiled_decode, (W, H))
+            return (upscale_host(upscaled_image, denoiser, tile_width, tile_height, padding, mask_blur,
+                                 force_uniform_tiles, device=dev, stats=self.last_stats),)
         if upscaled_image.is_cuda:
             image = upscaled_image.to(torch.float32)
         else:
@@ -116,7 +124,6 @@ class UltimateSDUpscaleDistributed:
         _, H, W, _ = image.shape
         denoiser = self._make_denoiser(model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler,
                                        denoise, tiled_decode, (W, H))
-        self.last_stats = {}
         if distributed:
             out = usdu_dist.upscale_static(image, denoiser, tile_width, tile_height, padding, mask_blur,
                                            force_uniform_tiles, stats=self.last_stats)
