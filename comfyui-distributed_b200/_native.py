@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 4
+ABI_VERSION = 5
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -25,6 +25,7 @@ T_FULL_X0, T_FULL_Y0, T_FULL_X1, T_FULL_Y1 = 16, 17, 18, 19
 TAB_HEADER = 8
 PACKED_ROW = 8
 FLAG_FAST = 1
+FILTER_LANCZOS, FILTER_BICUBIC = 0, 1
 CROP_ITEM_WORDS = 6
 BLEND_ITEM_WORDS = 4
 COVER_WORDS = 4
@@ -54,6 +55,11 @@ _SIGNATURES = {
     "usdu_resample_table_words": (c_int64, [c_int, c_int]),
     "usdu_build_resample_table": (c_int, [c_int, c_int, POINTER(c_int32)]),
     "usdu_build_identity_table": (c_int, [c_int, POINTER(c_int32)]),
+    "usdu_filter_ksize": (c_int, [c_int, c_int, c_int]),
+    "usdu_filter_table_words": (c_int64, [c_int, c_int, c_int]),
+    "usdu_build_filter_table": (c_int, [c_int, c_int, c_int, POINTER(c_int32)]),
+    "usdu_nearest_index": (c_int, [c_int, c_int, POINTER(c_int32)]),
+    "usdu_table_input_span": (c_int, [POINTER(c_int32), c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "usdu_box_blur_params": (c_int, [c_float, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
@@ -62,6 +68,11 @@ _SIGNATURES = {
     "usdu_t0_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p]),
     "usdu_mask_scratch_bytes": (c_int64, [POINTER(c_int32), c_int]),
     "usdu_build_feather_masks": (c_int, [POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
+    "usdu_plane_resample_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
+                                       c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64,
+                                       c_void_p]),
+    "usdu_plane_pad_fill_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "usdu_tile_crop_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "usdu_tile_blend": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -122,6 +133,31 @@ def build_resample_table(in_size: int, out_size: int) -> np.ndarray:
     return np.ascontiguousarray(tab)
 
 
+def build_filter_table(filt: int, in_size: int, out_size: int) -> np.ndarray:
+    """Generic-kernel table (header + bounds + kk) of a LANCZOS / BICUBIC axis; the packed rows
+    of the fast tile kernels are dropped."""
+    L = lib()
+    words = L.usdu_filter_table_words(filt, in_size, out_size)
+    if words < 0:
+        _check(int(words), "usdu_filter_table_words")
+    tab = np.zeros(int(words), dtype=np.int32)
+    _check(L.usdu_build_filter_table(filt, in_size, out_size, _i32p(tab)), "usdu_build_filter_table")
+    return np.ascontiguousarray(tab[: TAB_HEADER + out_size * (2 + int(tab[2]))])
+
+
+def nearest_index(in_size: int, out_size: int) -> np.ndarray:
+    idx = np.zeros(out_size, dtype=np.int32)
+    _check(lib().usdu_nearest_index(in_size, out_size, _i32p(idx)), "usdu_nearest_index")
+    return idx
+
+
+def table_input_span(table: np.ndarray, first_out: int, n_out: int):
+    a, b = c_int(), c_int()
+    _check(lib().usdu_table_input_span(_i32p(table), first_out, n_out, ctypes.byref(a), ctypes.byref(b)),
+           "usdu_table_input_span")
+    return a.value, b.value
+
+
 def build_identity_table(size: int) -> np.ndarray:
     tab = np.zeros(((TAB_HEADER + 3 * size + 3) & ~3) + size * PACKED_ROW, dtype=np.int32)
     _check(lib().usdu_build_identity_table(size, _i32p(tab)), "usdu_build_identity_table")
@@ -178,3 +214,16 @@ def tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_
                patch_h, src_ptr, src_is_u8, flags, stream):
     _check(lib().usdu_tile_blend(canvas_ptr, B, H, W, pitch, tiles_ptr, tabs_ptr, mask_ptr, items_ptr, n_items,
                                  cover_ptr, patch_w, patch_h, src_ptr, int(src_is_u8), flags, stream), "usdu_tile_blend")
+
+
+def plane_resample_u8(src_ptr, n, src_h, src_w, src_pitch, src_plane, tab_h_ptr, ox, ow, tab_v_ptr, oy, oh,
+                      mid_y0, mid_rows, mid_ptr, dst_ptr, dst_pitch, dst_plane, stream):
+    _check(lib().usdu_plane_resample_u8(src_ptr, n, src_h, src_w, src_pitch, src_plane, tab_h_ptr, ox, ow, tab_v_ptr,
+                                        oy, oh, mid_y0, mid_rows, mid_ptr, dst_ptr, dst_pitch, dst_plane, stream),
+           "usdu_plane_resample_u8")
+
+
+def plane_pad_fill_u8(src_ptr, n, h, w, src_pitch, src_plane, hp, vp, row_index_ptr, col_index_ptr, dst_ptr,
+                      dst_pitch, dst_plane, stream):
+    _check(lib().usdu_plane_pad_fill_u8(src_ptr, n, h, w, src_pitch, src_plane, hp, vp, row_index_ptr, col_index_ptr,
+                                        dst_ptr, dst_pitch, dst_plane, stream), "usdu_plane_pad_fill_u8")

@@ -63,32 +63,58 @@ static double lanczos_filter(double x) {
     return 0.0;
 }
 
-int usdu_resample_ksize(int in_size, int out_size) {
+static double bicubic_filter(double x) {
+    /* Keys cubic, a = -0.5, support 2 (Resample.c bicubic_filter; utils/usdu_utils.py:424,435) */
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+static double filter_support(int filter) { return filter == USDU_FILTER_BICUBIC ? 2.0 : 3.0; }
+
+int usdu_filter_ksize(int filter, int in_size, int out_size) {
     if (in_size <= 0 || out_size <= 0) {
-        usdu::set_error("usdu_resample_ksize: sizes must be positive (%d -> %d)", in_size, out_size);
+        usdu::set_error("usdu_filter_ksize: sizes must be positive (%d -> %d)", in_size, out_size);
+        return USDU_ERR_INVALID;
+    }
+    if (filter != USDU_FILTER_LANCZOS && filter != USDU_FILTER_BICUBIC) {
+        usdu::set_error("usdu_filter_ksize: unknown filter %d", filter);
         return USDU_ERR_INVALID;
     }
     double filterscale = (double)in_size / out_size;
     if (filterscale < 1.0) filterscale = 1.0;
-    double support = 3.0 * filterscale;
+    double support = filter_support(filter) * filterscale;
     return (int)ceil(support) * 2 + 1;
 }
 
-int64_t usdu_resample_table_words(int in_size, int out_size) {
-    int ks = usdu_resample_ksize(in_size, out_size);
+int usdu_resample_ksize(int in_size, int out_size) { return usdu_filter_ksize(USDU_FILTER_LANCZOS, in_size, out_size); }
+
+int64_t usdu_filter_table_words(int filter, int in_size, int out_size) {
+    int ks = usdu_filter_ksize(filter, in_size, out_size);
     if (ks < 0) return ks;
     // the packed rows are read with 128-bit loads: their start is padded to 4 int32
     return (((int64_t)USDU_TAB_HEADER + (int64_t)out_size * (2 + ks) + 3) & ~(int64_t)3) + (int64_t)out_size * 2 * USDU_PACKED_ROW;
 }
 
+int64_t usdu_resample_table_words(int in_size, int out_size) {
+    return usdu_filter_table_words(USDU_FILTER_LANCZOS, in_size, out_size);
+}
+
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
-    USDU_REQUIRE(table != nullptr, "usdu_build_resample_table: table is null");
-    int ksize = usdu_resample_ksize(in_size, out_size);
+    return usdu_build_filter_table(USDU_FILTER_LANCZOS, in_size, out_size, table);
+}
+
+int usdu_build_filter_table(int filter, int in_size, int out_size, int32_t* table) {
+    USDU_REQUIRE(table != nullptr, "usdu_build_filter_table: table is null");
+    int ksize = usdu_filter_ksize(filter, in_size, out_size);
     if (ksize < 0) return ksize;
+    double (*const weight)(double) = filter == USDU_FILTER_BICUBIC ? bicubic_filter : lanczos_filter;
     double scale, filterscale;
     scale = filterscale = (double)in_size / out_size;
     if (filterscale < 1.0) filterscale = 1.0;
-    const double support = 3.0 * filterscale;
+    const double support = filter_support(filter) * filterscale;
     const double ss = 1.0 / filterscale;
     table[0] = in_size;
     table[1] = out_size;
@@ -106,7 +132,7 @@ int usdu_build_resample_table(int in_size, int out_size, int32_t* table) {
         if (xmax > in_size) xmax = in_size;
         xmax -= xmin;
         for (int x = 0; x < xmax; x++) {
-            double v = lanczos_filter((x + xmin - center + 0.5) * ss);
+            double v = weight((x + xmin - center + 0.5) * ss);
             w[x] = v;
             ww += v;
         }
@@ -165,6 +191,24 @@ int usdu_build_identity_table(int size, int32_t* table) {
         int32_t* r = packed + (int64_t)i * USDU_PACKED_ROW;
         r[0] = i; r[1] = 1 << usdu::kPrecisionBits;
         for (int t = 1; t < USDU_FAST_TAPS; ++t) r[1 + t] = 0;
+    }
+    return USDU_OK;
+}
+
+// ---- Image.resize(..., NEAREST) source indices -------------------------------------
+int usdu_nearest_index(int in_size, int out_size, int32_t* index) {
+    USDU_REQUIRE(index != nullptr && in_size > 0 && out_size > 0, "usdu_nearest_index: bad arguments (%d -> %d)", in_size, out_size);
+    // Geometry.c ImagingScaleAffine: xo = a/2, then xo += a per sample (the additions accumulate
+    // in double exactly like the C loop), index = (int)xo.  utils/usdu_utils.py:190-199 stretches
+    // the edge strips of pad_image2 this way.
+    const double a = (double)in_size / out_size;
+    double xo = 0.0 + a * 0.5;
+    for (int x = 0; x < out_size; ++x) {
+        int xin = xo < 0.0 ? -1 : (int)xo;
+        if (xin < 0) xin = 0;
+        if (xin > in_size - 1) xin = in_size - 1;
+        index[x] = xin;
+        xo += a;
     }
     return USDU_OK;
 }

@@ -14,10 +14,13 @@ The tile pipeline treats the sampler as an injected callable on device tensors
 """
 from __future__ import annotations
 
+from contextlib import nullcontext
 from typing import List
 
 import numpy as np
 import torch
+
+from .model_patch import cropped_model_patches
 
 
 class T0Denoiser:
@@ -103,6 +106,11 @@ class ComfySampler:
         self.tiled_decode = tiled_decode and hasattr(comfy_nodes, "VAEDecodeTiled")
         self.image_size = image_size
         self.cond_cropper = cond_cropper
+        try:        # user cancel is polled once per tile like upscale/modes/static.py:326,407,476
+            import comfy.model_management as mm
+            self._poll_interrupt = mm.throw_exception_if_processing_interrupted
+        except ImportError:
+            self._poll_interrupt = None
 
     def __call__(self, tiles: torch.Tensor, rows: List) -> torch.Tensor:
         model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler, denoise = self.args
@@ -112,9 +120,16 @@ class ComfySampler:
             pos, neg = positive, negative
             if self.cond_cropper is not None:
                 pos, neg = self.cond_cropper(positive, negative, row, (px.shape[2], px.shape[1]), self.image_size)
+            if self._poll_interrupt is not None:
+                self._poll_interrupt()
             latent = self.n.VAEEncode().encode(vae, px)[0]
-            samples = self.n.common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, pos, neg, latent,
-                                             denoise=denoise)[0]
+            if self.image_size is not None:      # tile-local model patches (upscale/tile_ops.py:277)
+                ctx = cropped_model_patches(model, (row.x1, row.y1, row.x2, row.y2), self.image_size)
+            else:
+                ctx = nullcontext(model)
+            with ctx as tile_model:
+                samples = self.n.common_ksampler(tile_model, seed, steps, cfg, sampler_name, scheduler, pos, neg,
+                                                 latent, denoise=denoise)[0]
             if self.tiled_decode:
                 img = self.n.VAEDecodeTiled().decode(vae, samples, tile_size=512)[0]
             else:

@@ -445,12 +445,16 @@ class HostPipeline:
 
     @classmethod
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, n_bands: int) -> "HostPipeline":
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), n_bands, FORCE_GENERIC)
+        graph_safe = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
+        # a captured pipeline belongs to one sampler configuration; an eager one serves any sampler
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)) if graph_safe else "eager", n_bands, FORCE_GENERIC)
         hp = cls._cache.get(key)
         if hp is None or hp.dp is not dp:
             if len(cls._cache) > 2:
                 cls._cache.clear()
             hp = cls._cache[key] = HostPipeline(dp, B, denoiser, n_bands)
+        if not hp.graph_safe:
+            hp.denoiser = denoiser
         return hp
 
     def _rows(self, fn, y0: int, y1: int, src: torch.Tensor, dst: torch.Tensor, to_canvas: bool):
@@ -490,23 +494,33 @@ class HostPipeline:
             self.graphs[k] = g
         self.graphs[k].replay()
 
-    def run(self, host_in: torch.Tensor, host_out: torch.Tensor) -> torch.Tensor:
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor, stage: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """host_in pinned: bands are uploaded straight from it.  host_in pageable (what ComfyUI
+        usually hands over): pass a pinned `stage` buffer of the same shape -- each band is
+        memcpy'd into it by the host right before its upload is enqueued, so the host copy of
+        band k+1 overlaps the GPU's work on band k."""
         main = torch.cuda.current_stream(self.dp.device)
         self.canvas.launches = self.canvas.algo_bytes = 0
         self.launches = 0
         self.s_in.wait_stream(main)
         self.s_out.wait_stream(main)
-        ups = []
-        with torch.cuda.stream(self.s_in):
-            for band in self.bands:
-                y0, y1 = band["in"]
+
+        def upload(band):
+            y0, y1 = band["in"]
+            src = host_in
+            if stage is not None and y1 > y0:
+                stage[:, y0:y1].copy_(host_in[:, y0:y1])
+                src = stage
+            with torch.cuda.stream(self.s_in):
                 if y1 > y0:
-                    self.img[:, y0:y1].copy_(host_in[:, y0:y1], non_blocking=True)
+                    self.img[:, y0:y1].copy_(src[:, y0:y1], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record()
-                ups.append(e)
+            return e
+
+        ups = [upload(b) for b in self.bands] if stage is None else []
         for k, band in enumerate(self.bands):
-            main.wait_event(ups[k])
+            main.wait_event(ups[k] if stage is None else upload(band))
             self._rows(None, band["in"][0], band["in"][1], self.img, None, True)
             self._band_compute(k)
             f0, f1 = band["fin"]
@@ -548,26 +562,35 @@ class _PinnedPool:
 
 
 PINNED_RESULTS = _PinnedPool()
+PINNED_STAGING = _PinnedPool(keep=1)      # upload staging for pageable inputs (never handed out)
+MAX_BANDS = 12
 
 
 def upscale_host(host_image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
                  mask_blur: int, force_uniform_tiles: bool = True, device: Optional[torch.device] = None,
-                 stats: Optional[dict] = None, n_bands: int = 4) -> torch.Tensor:
-    """HOST tensor [B,H,W,3] fp32 -> HOST tensor (pinned), same result as upscale_single."""
+                 stats: Optional[dict] = None, n_bands: Optional[int] = None) -> torch.Tensor:
+    """HOST tensor [B,H,W,3] fp32 -> HOST tensor (pinned), same result as upscale_single.
+    n_bands: pipeline depth; default one band per tile row, at most MAX_BANDS (shorter fill/drain
+    of the two PCIe streams; the extra small launches hide under the copies)."""
     if host_image.is_cuda:
         raise ValueError("upscale_host takes a host tensor; use upscale_single for device tensors")
     device = device or torch.device("cuda", torch.cuda.current_device())
     x = host_image.to(torch.float32).contiguous()
-    if not x.is_pinned():
-        x = x.pin_memory()
     B, H, W, _ = x.shape
     plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
     with torch.cuda.device(device):
         dp = DevicePlan.get(plan, device)
+        if n_bands is None:
+            n_bands = min(len({t.y for t in plan.tiles}), MAX_BANDS)
         hp = HostPipeline.get(dp, B, denoiser, n_bands)
         out = PINNED_RESULTS.get(x.shape)
-        hp.run(x, out)
-        torch.cuda.current_stream(device).synchronize()
+        stage = None if x.is_pinned() else PINNED_STAGING.get(x.shape)
+        try:
+            hp.run(x, out, stage)
+            torch.cuda.current_stream(device).synchronize()
+        finally:
+            if not hp.graph_safe:
+                hp.denoiser = None      # do not keep the caller's MODEL / VAE alive in the cache
     if stats is not None:
         stats["gpu_launches"] = stats.get("gpu_launches", 0) + hp.canvas.launches + hp.launches
         stats["algo_bytes"] = stats.get("algo_bytes", 0) + hp.canvas.algo_bytes

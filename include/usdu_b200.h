@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 4
+#define USDU_ABI_VERSION 5
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -162,6 +162,16 @@ int usdu_resample_ksize(int in_size, int out_size);
 int64_t usdu_resample_table_words(int in_size, int out_size);
 /* fill `table` (host, usdu_resample_table_words() int32) */
 int usdu_build_resample_table(int in_size, int out_size, int32_t* table);
+/* The same for any of Pillow's separable filters used on the path: LANCZOS for the tiles
+ * (upscale/tile_ops.py:88,148,329), BICUBIC for conditioning masks (utils/usdu_utils.py:424,435). */
+#define USDU_FILTER_LANCZOS 0
+#define USDU_FILTER_BICUBIC 1
+int usdu_filter_ksize(int filter, int in_size, int out_size);
+int64_t usdu_filter_table_words(int filter, int in_size, int out_size);
+int usdu_build_filter_table(int filter, int in_size, int out_size, int32_t* table);
+/* source index of every output sample of Image.resize(..., NEAREST) along one axis
+ * (Geometry.c ImagingScaleAffine; used by pad_image2's edge strips, utils/usdu_utils.py:190-199) */
+int usdu_nearest_index(int in_size, int out_size, int32_t* index_host);
 /* table of an axis that keeps its size (size -> size): one tap of weight 2^22;
  * ((USDU_TAB_HEADER + 3*size + 3) & ~3) + size * USDU_PACKED_ROW int32.  Tables must start at a
  * multiple of 4 int32 in the pool (their packed rows are read with 128-bit loads). */
@@ -228,6 +238,30 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
                     const uint8_t* mask_pool_dev, const int32_t* items_dev, int n_items,
                     const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
                     int src_is_u8, int flags, void* stream);
+
+/* ---- one-channel u8 planes: per-tile conditioning masks (utils/usdu_utils.py:415-442) ---------
+ * Window of a separable 8bpc resize of n planes src[n][src_h][src_w] (Image.resize semantics:
+ * horizontal pass first, u8 intermediate, then vertical): dst[p][j][i] = resized[p][oy+j][ox+i]
+ * for j < oh, i < ow.  tab_h_dev / tab_v_dev are tables from usdu_build_filter_table for
+ * (src_w -> full output width) / (src_h -> full output height), or NULL when that axis keeps its
+ * size (Pillow skips the pass).  Only the window is computed, which gives exactly the
+ * pixels of "resize the whole mask to the canvas size, then crop" (crop_mask).
+ * The intermediate holds input rows mid_y0 .. mid_y0+mid_rows-1 (what the vertical taps of output
+ * rows oy..oy+oh-1 read: usdu_table_input_span on the HOST copy of the vertical table), layout
+ * [n][mid_rows][(ow+3)&~3] bytes; unused (may be NULL) unless both passes run. */
+int usdu_table_input_span(const int32_t* table_host, int first_out, int n_out, int* first_in, int* n_in);
+int usdu_plane_resample_u8(const uint8_t* src_dev, int n, int src_h, int src_w, int64_t src_pitch, int64_t src_plane,
+                           const int32_t* tab_h_dev, int ox, int ow, const int32_t* tab_v_dev, int oy, int oh,
+                           int mid_y0, int mid_rows, uint8_t* mid_dev,
+                           uint8_t* dst_dev, int64_t dst_pitch, int64_t dst_plane, void* stream);
+/* pad_image2(img, hp, hp, vp, vp, fill=True) (utils/usdu_utils.py:169-203) on n planes [h][w] ->
+ * [h+2vp][w+2hp]: left/right strips = edge column rows 1+row_index[y], then top/bottom strips =
+ * edge row columns 1+col_index[x] (they overwrite the corners).  row_index_dev = usdu_nearest_index
+ * (h-2 -> h+2vp), col_index_dev = usdu_nearest_index(w-2 -> w+2hp); either may be NULL when its
+ * pad is 0. */
+int usdu_plane_pad_fill_u8(const uint8_t* src_dev, int n, int h, int w, int64_t src_pitch, int64_t src_plane,
+                           int hp, int vp, const int32_t* row_index_dev, const int32_t* col_index_dev,
+                           uint8_t* dst_dev, int64_t dst_pitch, int64_t dst_plane, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

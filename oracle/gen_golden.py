@@ -7,6 +7,7 @@ Outputs (committed, small):
   tests/golden/single_*.npz       u8 outputs of the reference's process_single_gpu with
                                   the T0 denoiser (inputs are regenerated from seeds)
   tests/golden/prims.npz          create_tile_mask windows and blend_tile outputs
+  tests/golden/mask_crop.npz      crop_mask outputs (conditioning masks cut to a tile), u8
 
 Test infrastructure only (see oracle/usdu_oracle.py header).
 """
@@ -29,7 +30,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
-from inputs import make_input  # noqa: E402  (shared with the tests)
+from inputs import MASK_CROP_CASES, make_input, make_mask  # noqa: E402  (shared with the tests)
 
 
 def torch_t0(seed_unused=None):
@@ -82,8 +83,28 @@ SINGLE_CASES = [
 ]
 
 
+def gen_mask_crop():
+    """tests/golden/mask_crop.npz: the reference's crop_mask (utils/usdu_utils.py:415-442) on seeded masks."""
+    ref_loader.load()
+    U = sys.modules[ref_loader.PKG + ".utils.usdu_utils"]
+    out = {}
+    for (name, kind, seed, B, (Hm, Wm), region, canvas, tile) in MASK_CROP_CASES:
+        m = torch.from_numpy(make_mask(kind, seed, B, Hm, Wm))
+        d = {"mask": m.clone()}
+        U.crop_mask(d, region, canvas, canvas, tile, 0, 0)
+        res = d["mask"].numpy()
+        q = np.round(res * 255).astype(np.uint8)
+        assert np.array_equal(q.astype(np.float32) / np.float32(255), res)
+        out[name] = q
+        print("mask_crop", name, q.shape, hashlib.sha256(q.tobytes()).hexdigest()[:16])
+    np.savez_compressed(os.path.join(OUT, "mask_crop.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--mask-crop-only" in sys.argv:
+        return gen_mask_crop()
+    gen_mask_crop()
     node, fake_nodes = ref_loader.make_reference_node()
     fake_nodes.fn = torch_t0()
 

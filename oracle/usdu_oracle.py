@@ -157,20 +157,38 @@ def _lanczos3(x: float) -> float:
     return 0.0
 
 
-_COEFF_CACHE: Dict[Tuple[int, int], Tuple[np.ndarray, np.ndarray]] = {}
+def _bicubic(x: float) -> float:
+    """Resample.c bicubic_filter, a = -0.5 (Keys), support 2."""
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_FILTERS = {"lanczos": (_lanczos3, 3.0), "bicubic": (_bicubic, 2.0)}
+_COEFF_CACHE: Dict[Tuple[int, int, str], Tuple[np.ndarray, np.ndarray]] = {}
 
 
 def lanczos_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
+    return resample_coeffs(in_size, out_size, "lanczos")
+
+
+def resample_coeffs(in_size: int, out_size: int, filt: str = "lanczos") -> Tuple[np.ndarray, np.ndarray]:
     """precompute_coeffs + normalize_coeffs_8bpc for a full-axis resize (box = whole axis).
 
     Returns bounds int32[out,2] = (xmin, n) and kk int32[out, ksize] (22-bit fixed point)."""
-    key = (in_size, out_size)
+    key = (in_size, out_size, filt)
     if key in _COEFF_CACHE:
         return _COEFF_CACHE[key]
+    _lanczos3, fsupport = _FILTERS[filt]
     scale = filterscale = in_size / out_size
     if filterscale < 1.0:
         filterscale = 1.0
-    support = 3.0 * filterscale
+    support = fsupport * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     bounds = np.zeros((out_size, 2), dtype=np.int32)
     kk = np.zeros((out_size, ksize), dtype=np.int32)
@@ -200,10 +218,10 @@ def lanczos_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]
     return bounds, kk
 
 
-def _resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
+def _resample_axis0(img: np.ndarray, out_size: int, filt: str = "lanczos") -> np.ndarray:
     """One 8bpc resample pass along axis 0 of img[u8, n_in, ...]."""
     n_in = img.shape[0]
-    bounds, kk = lanczos_coeffs(n_in, out_size)
+    bounds, kk = resample_coeffs(n_in, out_size, filt)
     ksize = kk.shape[1]
     idx = bounds[:, 0:1] + np.arange(ksize, dtype=np.int32)[None, :]
     idx = np.minimum(idx, n_in - 1)  # taps past n have coefficient 0
@@ -217,17 +235,87 @@ def _resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
 
 
 def lanczos_resize_u8(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
-    """Image.resize((out_w, out_h), LANCZOS) on an u8 image [H, W, C] (or [H, W]).
+    return resize_u8(img, out_w, out_h, "lanczos")
+
+
+def resize_u8(img: np.ndarray, out_w: int, out_h: int, filt: str = "lanczos") -> np.ndarray:
+    """Image.resize((out_w, out_h), LANCZOS | BICUBIC) on an u8 image [H, W, C] (or [H, W]).
 
     Horizontal pass first with a u8 intermediate, then vertical; a pass is skipped when
     that axis keeps its size (Resample.c ImagingResampleInner)."""
     h, w = img.shape[:2]
     out = img
     if out_w != w:
-        out = np.swapaxes(_resample_axis0(np.swapaxes(out, 0, 1), out_w), 0, 1)
+        out = np.swapaxes(_resample_axis0(np.swapaxes(out, 0, 1), out_w, filt), 0, 1)
     if out_h != h:
-        out = _resample_axis0(out, out_h)
+        out = _resample_axis0(out, out_h, filt)
     return np.ascontiguousarray(out)
+
+
+# --------------------------------------------------------------------------------------
+# conditioning mask crop   (utils/usdu_utils.py:415-442, :242-266, :169-203)
+# --------------------------------------------------------------------------------------
+def nearest_index(in_size: int, out_size: int) -> np.ndarray:
+    """Source index of every output sample of Image.resize(..., NEAREST) along one axis
+    (Geometry.c ImagingScaleAffine: xo = a/2, then xo += a per sample, index = (int)xo --
+    the additions accumulate in double exactly like the C loop)."""
+    a = in_size / out_size
+    xo = 0.0 + a * 0.5
+    out = np.zeros(out_size, dtype=np.int32)
+    for x in range(out_size):
+        xin = -1 if xo < 0.0 else int(xo)
+        out[x] = min(max(xin, 0), in_size - 1)
+        xo += a
+    return out
+
+
+def pad_fill_u8(img: np.ndarray, hp: int, vp: int) -> np.ndarray:
+    """pad_image2(img, hp, hp, vp, vp, fill=True) on a mode-L image [h, w] (usdu_utils.py:169-203):
+    left/right columns = the edge column WITHOUT its first and last pixel, NEAREST-stretched to the
+    new height; then top/bottom rows likewise (they overwrite the corners)."""
+    h, w = img.shape
+    nh, nw = h + 2 * vp, w + 2 * hp
+    out = np.zeros((nh, nw), dtype=np.uint8)
+    out[vp:vp + h, hp:hp + w] = img
+    if hp > 0:
+        iy = 1 + nearest_index(h - 2, nh)
+        out[:, :hp] = img[iy, 0][:, None]
+        out[:, nw - hp:] = img[iy, w - 1][:, None]
+    if vp > 0:
+        ix = 1 + nearest_index(w - 2, nw)
+        out[:vp, :] = img[0, ix][None, :]
+        out[nh - vp:, :] = img[h - 1, ix][None, :]
+    return out
+
+
+def py_round(x: float) -> int:
+    return int(round(x))       # Python 3 round(): half to even, like the reference's call
+
+
+def mask_fit_geometry(cw: int, ch: int, pw: int, ph: int):
+    """resize_and_pad_image's sizes (usdu_utils.py:242-266): -> (rw, rh, hp, vp)."""
+    width_ratio, height_ratio = pw / cw, ph / ch
+    ratio = width_ratio if height_ratio > width_ratio else height_ratio
+    rw, rh = py_round(cw * ratio), py_round(ch * ratio)
+    return rw, rh, (pw - rw) // 2, (ph - rh) // 2
+
+
+def crop_mask_u8(mask: np.ndarray, region, canvas_size, tile_size) -> np.ndarray:
+    """crop_mask for ONE mask frame already cast to u8 [Hm, Wm] (usdu_utils.py:415-442):
+    BICUBIC to the canvas size, crop the region, LANCZOS to the tile's aspect-preserving size,
+    edge-fill pad, LANCZOS to the tile size, BICUBIC if that still is not the tile size."""
+    W, H = canvas_size
+    pw, ph = tile_size
+    x1, y1, x2, y2 = region
+    m = resize_u8(mask, W, H, "bicubic")[y1:y2, x1:x2]
+    ch, cw = m.shape
+    rw, rh, hp, vp = mask_fit_geometry(cw, ch, pw, ph)
+    m = resize_u8(m, rw, rh, "lanczos")
+    m = pad_fill_u8(m, hp, vp)
+    m = resize_u8(m, pw, ph, "lanczos")
+    if m.shape != (ph, pw):
+        m = resize_u8(m, pw, ph, "bicubic")
+    return m
 
 
 # --------------------------------------------------------------------------------------

@@ -21,3 +21,33 @@ def make_input(kind: str, seed: int, B: int, H: int, W: int) -> np.ndarray:
         img = np.stack([c, 1 - c, c], -1)[None].repeat(B, 0)
         return img.astype(np.float32)
     raise ValueError(kind)
+
+
+def make_mask(kind: str, seed: int, B: int, H: int, W: int) -> np.ndarray:
+    """Conditioning masks fp32 [B, H, W] in [0, 1] (NOT pre-quantised: the truncating cast is part
+    of what is tested)."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "noise":
+        return torch.rand(B, H, W, generator=g).numpy().astype(np.float32)
+    if kind == "blob":
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        out = []
+        for b in range(B):
+            cx, cy = (0.3 + 0.2 * b) * W, (0.6 - 0.1 * b) * H
+            r = np.sqrt((xx - cx) ** 2 + (yy - cy) ** 2) / (0.35 * max(W, H))
+            out.append(np.clip(1.2 - r, 0, 1) * (0.9 + 0.1 * torch.rand(H, W, generator=g).numpy()))
+        return np.stack(out).astype(np.float32)
+    raise ValueError(kind)
+
+
+# (name, kind, seed, B, (Hm, Wm), region, canvas (W, H), tile (pw, ph)) -- shared by oracle/gen_golden.py and the tests
+MASK_CROP_CASES = [
+    ("pad_v", "noise", 1, 2, (96, 64), (10, 20, 170, 150), (300, 260), (160, 136)),
+    ("interior_1080p", "blob", 2, 1, (135, 240), (480, 440, 1056, 1016), (1920, 1080), (544, 544)),
+    ("corner_pad_v", "noise", 3, 1, (64, 64), (0, 0, 300, 200), (512, 512), (304, 208)),
+    ("pad_h", "blob", 4, 2, (200, 100), (100, 37, 413, 260), (700, 500), (320, 224)),
+    ("tall_pad_h", "noise", 5, 1, (50, 50), (20, 10, 180, 300), (200, 320), (256, 256)),
+    ("last_tile_downscale", "noise", 6, 1, (300, 260), (724, 524, 1300, 1100), (1300, 1100), (544, 544)),
+    ("mask_is_canvas", "blob", 7, 1, (1100, 1300), (0, 0, 544, 544), (1300, 1100), (544, 544)),
+    ("upsample_tile", "noise", 8, 1, (90, 160), (992, 512, 1280, 800), (1280, 800), (544, 544)),
+]

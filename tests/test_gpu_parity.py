@@ -256,14 +256,18 @@ def test_full_size_properties_cfg2():
     assert np.array_equal((a[safe].cpu().numpy() * 255).round().astype(np.uint8), cu8[safe])
 
 
-@pytest.mark.parametrize("n_bands", [1, 2, 4, 9])
+@pytest.mark.parametrize("n_bands", [1, 2, 4, 9, None])
 @pytest.mark.parametrize("kind,B,H,W,tile,pad,blur", [("noise", 1, 600, 420, 128, 16, 8), ("smooth", 5, 300, 260, 64, 32, 40),
                                                       ("noise", 1, 333, 777, 64, 128, 8)])
 def test_host_pipeline_matches_oracle(kind, B, H, W, tile, pad, blur, n_bands):
     """Band-pipelined host path (overlapped upload / kernels / download, a different topological
-    order of the same DAG) == the sequential reference semantics."""
+    order of the same DAG) == the sequential reference semantics; pageable inputs (staged band by
+    band through a pinned buffer) and pinned inputs (uploaded in place)."""
     img = make_input(kind, 13, B, H, W)
     ref = orc.process_single(img, orc.make_t0_denoiser(5, 0.4), tile, tile, pad, blur, True)
-    for _ in range(2):                                   # second call replays the captured band graphs
-        out = engine.upscale_host(torch.from_numpy(img), T0Denoiser(5, 0.4), tile, tile, pad, blur, True, n_bands=n_bands)
-        assert not out.is_cuda and np.array_equal(out.numpy(), ref)
+    for pinned in (False, True, False):                  # later calls replay the captured band graphs
+        x = torch.from_numpy(img.copy())
+        x = x.pin_memory() if pinned else x
+        out = engine.upscale_host(x, T0Denoiser(5, 0.4), tile, tile, pad, blur, True, n_bands=n_bands)
+        assert not out.is_cuda and out.is_pinned() and np.array_equal(out.numpy(), ref)
+        assert np.array_equal(x.numpy(), img)            # the caller's tensor is never written

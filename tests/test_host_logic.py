@@ -73,6 +73,40 @@ def test_resample_table_equals_oracle(n_in, n_out):
         assert tab[3] > 15
 
 
+@pytest.mark.parametrize("filt,name", [(0, "lanczos"), (1, "bicubic")])
+@pytest.mark.parametrize("n_in,n_out", [(64, 300), (300, 64), (135, 1080), (576, 544), (7, 63), (960, 7680)])
+def test_filter_table_equals_oracle(filt, name, n_in, n_out):
+    tab = nat.build_filter_table(filt, n_in, n_out)
+    bounds, kk = orc.resample_coeffs(n_in, n_out, name)
+    H, ks = nat.TAB_HEADER, kk.shape[1]
+    assert (tab[0], tab[1], tab[2]) == (n_in, n_out, ks)
+    assert np.array_equal(tab[H:H + 2 * n_out].reshape(n_out, 2), bounds)
+    assert np.array_equal(tab[H + 2 * n_out:].reshape(n_out, ks), kk)
+    lo, n = nat.table_input_span(tab, n_out // 3, max(1, n_out // 2))
+    b = bounds[n_out // 3:n_out // 3 + max(1, n_out // 2)]
+    assert lo == b[:, 0].min() and lo + n == (b[:, 0] + b[:, 1]).max()
+
+
+def test_filter_table_rejects_unknown_filter_and_span_outside_table():
+    with pytest.raises(nat.NativeError):
+        nat.build_filter_table(7, 10, 20)
+    with pytest.raises(nat.NativeError):
+        nat.table_input_span(nat.build_filter_table(1, 10, 20), 15, 10)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(5, 17), (542, 576), (30, 7), (100, 100), (3, 1000), (1, 4)])
+def test_nearest_index_equals_oracle(n_in, n_out):
+    assert np.array_equal(nat.nearest_index(n_in, n_out), orc.nearest_index(n_in, n_out))
+
+
+def test_mask_fit_geometry_equals_oracle():
+    from comfyui_distributed_b200.conditioning import mask_fit_geometry
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        cw, ch, pw, ph = (int(v) for v in rng.integers(8, 700, 4))
+        assert mask_fit_geometry(cw, ch, pw, ph) == orc.mask_fit_geometry(cw, ch, pw, ph)
+
+
 def test_identity_table():
     tab = nat.build_identity_table(5)
     assert tab[4] % 4 == 0 and tab.shape[0] % 4 == 0

@@ -45,3 +45,15 @@ def test_process_single_matches_reference(case):
     ref = np.load(os.path.join(G, f"single_{case['name']}.npz"))["out"]
     assert hashlib.sha256(ref.tobytes()).hexdigest() == case["sha256"]
     assert np.array_equal(out, ref)
+
+
+def test_mask_crop_matches_reference():
+    """oracle.crop_mask_u8 == the reference's crop_mask (utils/usdu_utils.py:415-442), fixtures from
+    oracle/gen_golden.py."""
+    from inputs import MASK_CROP_CASES, make_mask
+    gold = np.load(os.path.join(G, "mask_crop.npz"))
+    for (name, kind, seed, B, (Hm, Wm), region, canvas, tile) in MASK_CROP_CASES:
+        m = make_mask(kind, seed, B, Hm, Wm)
+        for b in range(B):
+            got = orc.crop_mask_u8(orc.quantize_u8(m[b]), region, canvas, tile)
+            assert np.array_equal(got, gold[name][b]), name
