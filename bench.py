@@ -353,13 +353,16 @@ def main():
             "config": {"workload": args.workload, "canvas": [B, H, W], "tile": tile, "padding": pad, "mask_blur": blur,
                        "tiles": stats.get("tiles"), "waves": stats.get("waves"), "denoiser": den_name,
                        "semantics": "exact progressive (single_gpu)" if world == 1 else "static replay, fixed partition",
-                       "cuda_graph": bool(world == 1 and engine.USE_CUDA_GRAPHS and getattr(den, "cuda_graph_safe", False)),
+                       "cuda_graph": bool(engine.USE_CUDA_GRAPHS and getattr(den, "cuda_graph_safe", False)),
+                       "transport": stats.get("transport"),
                        "l2": "inputs larger than L2 (canvas 99.5 MB u8 + 398 MB fp32 image per step)"},
             "clocks": clk,
             "e2e": {"value": mp / (e2e_ms * 1e-3), "unit": "MP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
                     "api": "UltimateSDUpscaleDistributed.run(host tensor) -> host tensor",
-                    "note": "N=1: upload, kernels and download overlap band by band (engine.HostPipeline)"},
+                    "note": ("upload, kernels and download overlap band by band (engine.HostPipeline)" if world == 1 else
+                             "every rank uploads the replicated canvas (like the reference's workers), rank 0 downloads the result; "
+                             "copies are serial around the distributed job")},
             "gpu_launches": stats.get("gpu_launches", 0) * args.steps,
             "gpu_launches_per_step": stats.get("gpu_launches", 0),
             "roofline": roofline}

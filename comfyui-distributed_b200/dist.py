@@ -71,6 +71,71 @@ def tile_payload_layout(plan, assignment: Sequence[Sequence[int]], B: int):
     return where, sizes
 
 
+# --------------------------------------------------------------------------------------
+# peer transport: the master's blend kernel pulls worker tiles straight out of the workers'
+# HBM over NVLink (no gather step, no staging copy; the transfer overlaps the blend math CTA
+# by CTA).  The payload buffers are symmetric allocations (same size on every rank) whose
+# device addresses are exchanged once by torch's symmetric-memory rendezvous; inside one
+# unified virtual address space a tile of rank r is simply  own_base + (ptr[r] - ptr[own]) +
+# offset, which the blend kernel's 64-bit source offsets already express.
+# --------------------------------------------------------------------------------------
+import os
+
+USE_PEER_BLEND = os.environ.get("USDU_PEER_BLEND", "1") != "0"
+
+
+def peer_offsets(order: Sequence[int], where: Dict[int, Tuple[int, int]], ptrs: Sequence[int], own_rank: int) -> np.ndarray:
+    """Byte offset, relative to this rank's payload base, of every tile of `order` inside its
+    owner's payload buffer (ptrs[r] = device address of rank r's buffer as mapped HERE)."""
+    base = int(ptrs[own_rank])
+    return np.array([int(ptrs[where[t][0]]) - base + where[t][1] for t in order], dtype=np.int64)
+
+
+class PeerPayload:
+    """Symmetric u8 buffer + rendezvous handle, cached per (bytes, device, group)."""
+
+    _cache: Dict[tuple, Optional["PeerPayload"]] = {}
+
+    def __init__(self, nbytes: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else td.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.buf.zero_()
+
+    def barrier(self, channel: int = 0):
+        """Stream-ordered barrier over all ranks (signal pads in peer memory, system-scope
+        release/acquire): kernels enqueued before it on any rank are complete and visible to
+        kernels enqueued after it on every rank."""
+        self.hdl.barrier(channel=channel, timeout_ms=20000)
+
+    @classmethod
+    def get(cls, nbytes: int, device, group) -> Optional["PeerPayload"]:
+        """Collective.  Returns None on EVERY rank if any rank cannot set the buffer up (no
+        NVLink/P2P, symmetric memory unsupported) -- the caller then uses the NCCL all-gather."""
+        if not (USE_PEER_BLEND and td.is_initialized() and td.get_backend(group) == "nccl"):
+            return None
+        key = (int(nbytes), str(device), id(group))
+        if key in cls._cache:
+            return cls._cache[key]
+        obj, ok = None, 1
+        try:
+            obj = PeerPayload(int(nbytes), device, group)
+        except Exception as e:     # noqa: BLE001 -- any failure means "transport not available here"
+            ok = 0
+            cls.last_error = repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            obj = None
+        if len(cls._cache) > 4:
+            cls._cache.clear()
+        cls._cache[key] = obj
+        return obj
+
+    last_error: Optional[str] = None
+
+
 def final_blend_order(assignment: Sequence[Sequence[int]]) -> List[int]:
     """Tile ids of all NON-master participants in the order the master composites them
     (ascending tile id, upscale/modes/static.py:521-526)."""
@@ -108,28 +173,35 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         sizes = [max(sz, 16) for sz in sizes]
         graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
         payload = None
+        peer = PeerPayload.get((max(sizes) + 255) // 256 * 256, image.device, group) if world > 1 else None
+        if world > 1:
+            payload = (peer.buf[: sizes[rank]] if peer is not None
+                       else _payload_buffer(sizes[rank], image.device))
         if graphed:      # this rank's wave loop (crop -> sampler -> local blend -> u8 pack) as one CUDA graph
-            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank],
-                                       payload_bytes=sizes[rank] if world > 1 else 0, where=where)
-            canvas, payload, base = gw.replay(image), gw.payload, None
+            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank], payload=payload, where=where)
+            canvas, base = gw.replay(image), None
         else:
             canvas = Canvas(dp, B).load(image)
             base = canvas.clone() if (all_ranks_result and rank != 0) else None
-            if world > 1:
-                payload = torch.zeros(sizes[rank], dtype=torch.uint8, device=image.device)
             run_progressive(canvas, asg[rank], denoiser, payload=payload, where=where)
         if world > 1:
-            gathered, _ = all_gather_bytes(payload, group, sizes=sizes)
-            cap = gathered.shape[1]
-            if rank == 0 or all_ranks_result:
-                target = canvas
-                order = final_blend_order(asg)
-                if rank != 0:
-                    # rebuild the master's canvas: base + master tiles in the master's order
-                    target = base
-                    order = list(asg[0]) + order
-                offs = np.array([where[t][0] * cap + where[t][1] for t in order], dtype=np.int64)
-                target.blend(order, gathered.view(-1), offs)
+            produce_here = rank == 0 or all_ranks_result
+            target, order = canvas, final_blend_order(asg)
+            if produce_here and rank != 0:
+                # rebuild the master's canvas: base + master tiles in the master's order
+                target, order = base, list(asg[0]) + order
+            if peer is not None:
+                peer.barrier(0)                          # every payload is complete and visible
+                if produce_here:
+                    target.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank))
+                peer.barrier(1)                          # nobody refills its payload while it is being read
+            else:
+                gathered, _ = all_gather_bytes(payload, group, sizes=sizes)
+                cap = gathered.shape[1]
+                if produce_here:
+                    offs = np.array([where[t][0] * cap + where[t][1] for t in order], dtype=np.int64)
+                    target.blend(order, gathered.view(-1), offs)
+            if produce_here:
                 canvas = target
         produce = rank == 0 or all_ranks_result
         res = canvas.result() if produce else image
@@ -139,7 +211,21 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         stats["tiles"] = len(plan.tiles)
         stats["tiles_this_rank"] = len(asg[rank])
         stats["conflict_free"] = plan.conflict_free(asg)
+        stats["transport"] = "single" if world == 1 else ("nvlink peer loads" if peer is not None else "nccl all_gather")
     return res
+
+
+_PAYLOADS: Dict[tuple, torch.Tensor] = {}
+
+
+def _payload_buffer(nbytes: int, device) -> torch.Tensor:
+    """Reused send buffer of the NCCL transport (stable address: it is baked into the wave graph)."""
+    key = (int(nbytes), str(device))
+    if key not in _PAYLOADS:
+        if len(_PAYLOADS) > 8:
+            _PAYLOADS.clear()
+        _PAYLOADS[key] = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+    return _PAYLOADS[key]
 
 
 def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int, mask_blur: int,

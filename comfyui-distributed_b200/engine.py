@@ -318,14 +318,14 @@ class GraphedWaves:
     _cache: Dict[tuple, "GraphedWaves"] = {}
 
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
-                 order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
-                 where: Optional[dict] = None, skip: Sequence[str] = ()):
+                 order: Optional[Sequence[int]] = None, keep_processed: bool = False,
+                 payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()):
         global PROFILE
         self.canvas = Canvas(dp, B)
         self.denoiser = denoiser
         order = list(range(len(dp.plan.tiles))) if order is None else list(order)
         self.shipped: Dict[int, torch.Tensor] = {}
-        self.payload = (torch.zeros(payload_bytes, dtype=torch.uint8, device=dp.device) if payload_bytes else None)
+        self.payload = payload        # caller-owned transport buffer the packed u8 tiles are written into
         self.canvas.buf.zero_()
         side = torch.cuda.Stream(device=dp.device)
         side.wait_stream(torch.cuda.current_stream(dp.device))
@@ -353,15 +353,16 @@ class GraphedWaves:
 
     @classmethod
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None,
-            order: Optional[Sequence[int]] = None, keep_processed: bool = False, payload_bytes: int = 0,
-            where: Optional[dict] = None, skip: Sequence[str] = ()) -> "GraphedWaves":
+            order: Optional[Sequence[int]] = None, keep_processed: bool = False,
+            payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()) -> "GraphedWaves":
+        pkey = None if payload is None else (payload.data_ptr(), payload.numel())
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC,
-               None if order is None else tuple(order), keep_processed, payload_bytes, tuple(skip))
+               None if order is None else tuple(order), keep_processed, pkey, tuple(skip))
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
             if len(cls._cache) > 6:
                 cls._cache.clear()
-            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload_bytes, where, skip)
+            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip)
         return gw
 
     def replay(self, image: torch.Tensor) -> Canvas:

@@ -161,3 +161,16 @@ def _w_static_bookkeeping(rank, world):
 
 def test_static_transport_two_ranks():
     _run(_w_static_bookkeeping, 2)
+
+
+def test_peer_offsets_address_every_owner_buffer():
+    """Offsets handed to the blend kernel in peer mode = distance between the buffers' device
+    addresses (as mapped on the reading rank) + the tile's slot inside its owner's payload."""
+    from comfyui_distributed_b200 import dist as udist
+    where = {0: (0, 0), 1: (1, 0), 2: (2, 16), 3: (1, 4096), 4: (0, 2048)}
+    ptrs = [0x7F0000000000, 0x7F0040000000, 0x7E0000000000]          # rank 2's buffer is mapped BELOW the reader's
+    offs = udist.peer_offsets([1, 2, 3], where, ptrs, own_rank=0)
+    assert offs.dtype == np.int64
+    assert list(offs) == [0x40000000, 0x7E0000000000 - 0x7F0000000000 + 16, 0x40000000 + 4096]
+    assert list(udist.peer_offsets([0, 4], where, ptrs, own_rank=0)) == [0, 2048]
+    assert list(udist.peer_offsets([1], where, ptrs, own_rank=1)) == [0]
