@@ -137,7 +137,7 @@ __device__ __forceinline__ void load_job(int32_t* job_sm, const int32_t* __restr
 }
 
 __device__ __forceinline__ void stage_rows_v(int32_t* rows_sm, const int32_t* __restrict__ tabs, const JobView& J) {
-    const int q = (J[USDU_J_TAPS_V] + 1) / 4;                        // int4 per packed row: 2 or 4
+    const int q = J[USDU_J_TAPS_V] <= USDU_FAST_TAPS ? 2 : 4;        // int4 per packed row (8 or 16 int32)
     for (int i = threadIdx.x; i < FBH * q; i += kT) {
         const int r = i / q, part = i - r * q;
         const int o = clampi(J[USDU_J_OY_BASE] + r, 0, J[USDU_J_N_OUT_V] - 1);
@@ -153,6 +153,8 @@ __device__ __forceinline__ PackedRow<TAPS> load_row_h(const int32_t* __restrict_
     return read_row<TAPS>([&](int i) { return __ldg(p + i); });
 }
 
+constexpr int kUpTaps = 6;   // taps of an up-scaling (or size-keeping) LANCZOS axis: blend of every uniform tile
+
 // stage -> (sync) -> H pass for one job; the tap count of the axis picks the instantiation
 template <class Stage>
 __device__ __forceinline__ void stage_and_hpass(const int32_t* __restrict__ tabs, const JobView& J, uint32_t* in, uint8_t* mid,
@@ -161,7 +163,10 @@ __device__ __forceinline__ void stage_and_hpass(const int32_t* __restrict__ tabs
         const PackedRow<USDU_FAST_TAPS> rh = load_row_h<USDU_FAST_TAPS>(tabs, J);    // in flight during staging
         stage();
         __syncthreads();
-        hpass<USDU_FAST_TAPS>(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+        if (J[USDU_J_TAPS_H] <= kUpTaps)
+            hpass<USDU_FAST_TAPS, kUpTaps>(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
+        else
+            hpass<USDU_FAST_TAPS>(in, mid, rh, J[USDU_J_IX0], J[USDU_J_ROWS], xw);
     } else {
         const PackedRow<MAXTAPS> rh = load_row_h<MAXTAPS>(tabs, J);
         stage();
@@ -172,10 +177,12 @@ __device__ __forceinline__ void stage_and_hpass(const int32_t* __restrict__ tabs
 
 template <class Epilogue>
 __device__ __forceinline__ void vpass_any(const uint8_t* mid, const int32_t* rows_v, const JobView& J, Epilogue& epi, int r0, int r1) {
-    if (J[USDU_J_TAPS_V] <= USDU_FAST_TAPS)
-        vpass<USDU_FAST_TAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
+    if (J[USDU_J_TAPS_V] <= kUpTaps)
+        vpass<USDU_FAST_TAPS, kUpTaps>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
+    else if (J[USDU_J_TAPS_V] <= USDU_FAST_TAPS)
+        vpass<USDU_FAST_TAPS, USDU_FAST_TAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
     else
-        vpass<MAXTAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
+        vpass<MAXTAPS, MAXTAPS>(mid, rows_v, J[USDU_J_IY0], epi, r0, r1);
 }
 
 // ======================================================================================

@@ -61,13 +61,15 @@ __device__ __forceinline__ uint32_t finish(int acc) {
     return (uint32_t)__vimin_s32_relu(acc >> kPrecisionBits, 255);
 }
 
-// 4 lines x TAPS taps: words w[t] hold the 4 lines' bytes of tap t
-template <int TAPS>
-__device__ __forceinline__ void dot4(const uint32_t (&w)[TAPS], const PackedRow<TAPS>& row, int (&acc)[R]) {
+// 4 lines x N taps: words w[t] hold the 4 lines' bytes of tap t.  N <= TAPS is the number of taps
+// the axis really uses (an up-scaling LANCZOS axis has exactly 6: int(c+3.5) - int(c-2.5); the
+// 7th slot of its packed row is always 0 and is not multiplied).
+template <int TAPS, int N>
+__device__ __forceinline__ void dot4(const uint32_t (&w)[N], const PackedRow<TAPS>& row, int (&acc)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 1 << (kPrecisionBits - 1);
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) {
+    for (int t = 0; t < N; ++t) {
         // (moving one of the four extractions to the integer-FMA pipe with IMAD.HI -- hi32(w*2^8)
         // == w >> 24 -- was measured and is slower: crop +4 %, blend +6 %)
 #pragma unroll
@@ -86,7 +88,7 @@ struct JobView {
 
 // ---- H pass: in (planar, row packed) -> mid[row][block px * 3 + c] ----------------------
 // `row` = this thread's pixel column coefficients (loaded from global before staging).
-template <int TAPS>
+template <int TAPS, int N = TAPS>
 __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* __restrict__ mid, const PackedRow<TAPS>& row,
                                       int ix0, int rows_in, int xw) {
     const int px = threadIdx.x % FBW, sub = threadIdx.x / FBW;
@@ -96,11 +98,11 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* 
 #pragma unroll 2
     for (int u = sub; u < units; u += kT / FBW) {
         const uint32_t* wp = w0 + (size_t)u * xw;
-        uint32_t w[TAPS];
+        uint32_t w[N];
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) w[t] = wp[t];
+        for (int t = 0; t < N; ++t) w[t] = wp[t];
         int acc[R];
-        dot4(w, row, acc);
+        dot4<TAPS, N>(w, row, acc);
         const int g = u / 3, c = u - g * 3;
         uint8_t* oo = o + (size_t)(4 * g) * MID_PITCH + c;
 #pragma unroll
@@ -112,7 +114,7 @@ __device__ __forceinline__ void hpass(const uint32_t* __restrict__ in, uint8_t* 
 // rows_v: shared-memory copy of the packed rows of block rows 0..FBH-1.
 // Epilogue::prefetch(block_row, strip) issues the loads the epilogue will need (feather alpha)
 // BEFORE the multiply-adds, Epilogue::row(pre, block_row, strip, s) consumes them.
-template <int TAPS, class Epilogue>
+template <int TAPS, int N, class Epilogue>
 __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int32_t* rows_v, int iy0, Epilogue& epi,
                                       int row_begin, int row_end) {
     constexpr int STRIPS = FBW * 3 / 4;             // 96
@@ -125,11 +127,11 @@ __device__ __forceinline__ void vpass(const uint8_t* __restrict__ mid, const int
         const PackedRow<TAPS> row = read_row<TAPS>([&](int i) { return rp[i]; });
         const uint8_t* m = mid + (size_t)(row.first - iy0) * MID_PITCH + 4 * strip;
         const typename Epilogue::Pre pre = epi.prefetch(r, strip);
-        uint32_t w[TAPS];
+        uint32_t w[N];
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) w[t] = *reinterpret_cast<const uint32_t*>(m + (size_t)t * MID_PITCH);
+        for (int t = 0; t < N; ++t) w[t] = *reinterpret_cast<const uint32_t*>(m + (size_t)t * MID_PITCH);
         int acc[R];
-        dot4(w, row, acc);
+        dot4<TAPS, N>(w, row, acc);
         uint32_t s[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) s[q] = finish(acc[q]);

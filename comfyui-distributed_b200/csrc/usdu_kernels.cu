@@ -42,34 +42,34 @@ quantize_canvas_kernel(const float* __restrict__ img, uint8_t* __restrict__ canv
     }
 }
 
+// One thread turns ONE canvas word (4 bytes) into one float4: consecutive lanes read consecutive
+// words (128 B per warp load) and write consecutive float4 (512 B per warp store, every 32-byte
+// sector written whole by one instruction).  Rows on blockIdx.y, no integer division.
 __global__ void __launch_bounds__(kThreads)
 dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__ img, int rows, int W3,
                          int64_t pitch, int vec_ok) {
-    const int chunks = (W3 + 15) >> 4;
-    const int64_t total = (int64_t)rows * chunks;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / chunks;
-        const int j0 = (int)(i - row * chunks) << 4;
-        const uint8_t* src = canvas + row * pitch + j0;
-        float* dst = img + row * W3 + j0;
-        if (vec_ok && j0 + 16 <= W3) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+    if (vec_ok) {
+        const int words = W3 >> 2;
+        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(canvas + (int64_t)row * pitch);
+            float4* dst = reinterpret_cast<float4*>(img + (int64_t)row * W3);
+#pragma unroll 4
+            for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+                const uint32_t v = __ldcs(src + w);
                 float4 o;
-                o.x = dequant_u8_fast(w[k] & 0xFF);
-                o.y = dequant_u8_fast((w[k] >> 8) & 0xFF);
-                o.z = dequant_u8_fast((w[k] >> 16) & 0xFF);
-                o.w = dequant_u8_fast(w[k] >> 24);
-                __stcs(d4 + k, o);
+                o.x = dequant_u8_fast(v & 0xFF);
+                o.y = dequant_u8_fast((v >> 8) & 0xFF);
+                o.z = dequant_u8_fast((v >> 16) & 0xFF);
+                o.w = dequant_u8_fast(v >> 24);
+                __stcs(dst + w, o);
             }
-        } else {
-            const int n = min(16, W3 - j0);
-            for (int k = 0; k < n; ++k) dst[k] = dequant_u8_fast(src[k]);
         }
+        return;
+    }
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint8_t* src = canvas + (int64_t)row * pitch;
+        float* dst = img + (int64_t)row * W3;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W3; j += gridDim.x * blockDim.x) dst[j] = dequant_u8_fast(src[j]);
     }
 }
 
@@ -466,9 +466,14 @@ int usdu_dequantize_canvas(const uint8_t* canvas_dev, float* img_dev, int B, int
     USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_dequantize_canvas: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
     const int W3 = W * 3;
     const int vec_ok = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0) && (((uintptr_t)canvas_dev & 15) == 0);
-    const int64_t total = (int64_t)B * H * ((W3 + 15) / 16);
-    const int grid = grid_for((total + kThreads - 1) / kThreads);
-    dequantize_canvas_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * H, W3, pitch, vec_ok);
+    const int per_row = vec_ok ? W3 / 4 : W3;
+    int gx = (per_row + kThreads * 4 - 1) / (kThreads * 4);          // ~4 items per thread along a row
+    if (gx < 1) gx = 1;
+    int64_t gy = (int64_t)B * H;
+    if (gy > 65535) gy = 65535;
+    if (gy * gx > 148 * 16) gy = (148 * 16 + gx - 1) / gx;
+    if (gy < 1) gy = 1;
+    dequantize_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * H, W3, pitch, vec_ok);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

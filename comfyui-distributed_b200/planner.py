@@ -145,6 +145,7 @@ class Plan:
     _tab_packed: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_first: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
     _tab_taps: Dict[Tuple[int, int], int] = field(default_factory=dict)
+    _tab_job_taps: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _gblock: Optional[Tuple[int, int]] = None
 
     # ---- construction ---------------------------------------------------------------
@@ -176,6 +177,9 @@ class Plan:
             self._tab_packed[key] = off + int(tab[4])          # pool index of packed row 0 (fast kernels)
             taps = int(tab[6]) - 1 if tab[4] else int(tab[3])  # 7 or 15 staged taps per output on the fast path
             self._tab_taps[key] = taps
+            # what the job records carry: the real maximum when it is below the 7-slot row (an up-scaling
+            # LANCZOS axis uses exactly 6), so the kernels can skip the always-zero last slot
+            self._tab_job_taps[key] = min(taps, max(int(tab[3]), 1)) if taps <= nat.FAST_TAPS else taps
             b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
             self._tab_first[key] = b[:, 0].astype(np.int64)
             self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], taps)], 1)   # [lo, hi) per output
@@ -448,12 +452,12 @@ class Plan:
             m = (ew == key[0]) & (pw == key[1])
             ix0[m] = self._first(key, ox0[m])
             ix1[m] = np.minimum(self._first(key, ox0[m] + nat.FAST_BLOCK_W - 1) + self._tab_taps[key], key[0])
-            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_taps[key]
+            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_job_taps[key]
         for key in {(int(a), int(b)) for a, b in zip(eh, ph)}:
             m = (eh == key[0]) & (ph == key[1])
             iy0[m] = self._first(key, oy0[m])
             iy1[m] = np.minimum(self._first(key, oy0[m] + bh[m] - 1) + self._tab_taps[key], key[0])
-            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_taps[key]
+            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_job_taps[key]
         J[:, nat.J_TAPS_H], J[:, nat.J_TAPS_V] = taps_h, taps_v
         px_abs = x1 + ix0
         lead = px_abs & 3
@@ -540,12 +544,12 @@ class Plan:
             m = (pw == key[0]) & (ew == key[1])
             ix0[m] = self._first(key, ox_base[m])
             ix1[m] = np.minimum(self._first(key, ox_base[m] + bw - 1) + self._tab_taps[key], key[0])
-            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_taps[key]
+            rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_job_taps[key]
         for key in {(int(a), int(b)) for a, b in zip(ph, eh)}:
             m = (ph == key[0]) & (eh == key[1])
             iy0[m] = self._first(key, oy_base[m])
             iy1[m] = np.minimum(self._first(key, oy_base[m] + bh - 1) + self._tab_taps[key], key[0])
-            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_taps[key]
+            rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_job_taps[key]
         lead = ix0 & 3
         J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
         J[:, nat.J_TAPS_H], J[:, nat.J_TAPS_V] = taps_h, taps_v

@@ -133,7 +133,8 @@ typedef enum usdu_status {
 #define USDU_J_FRAME_LO 26 /* elements per frame PH*PW*3 */
 #define USDU_J_FRAME_HI 27
 #define USDU_J_NEXT 28     /* blend: index of the next record of the same block, -1 = last */
-#define USDU_J_TAPS_H 29   /* taps of the horizontal / vertical axis: USDU_FAST_TAPS or USDU_FAST_TAPS_WIDE */
+#define USDU_J_TAPS_H 29   /* taps of the horizontal / vertical axis: 1..USDU_FAST_TAPS (packed rows of 8 int32; a value
+                              <= 6 lets the kernel skip the unused last slot) or USDU_FAST_TAPS_WIDE (rows of 16) */
 #define USDU_J_TAPS_V 30
 
 /* Feather-mask spec (host array, USDU_MASK_WORDS int32 each). */
