@@ -331,7 +331,7 @@ template <bool kSrcU8>
 __global__ void __launch_bounds__(kT, 4)
 blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
                   const int32_t* __restrict__ jobs, const void* __restrict__ src_v, int W3, int patch_w, int patch_h,
-                  int block_rows, int dbg, const __grid_constant__ CUtensorMap cmap) {
+                  int block_rows, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     // [canvas block: 2 boxes x block_rows x 192] [job, rows_v] [bar] [in] [mid]
     const size_t dbytes = (size_t)2 * block_rows * kDBox;
@@ -367,11 +367,7 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
             stage_rows_v(rows_v, tabs, J);
         }
         const int64_t first_el = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
-        if (dbg & 2) {       // timing experiment: no H pass
-            if (!(dbg & 1)) stage_f32(in, xw, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS], J[USDU_J_COLS], J[USDU_J_LEAD]);
-        } else
         stage_and_hpass(tabs, J, in, mid, xw, [&]() {
-            if (dbg & 1) return;   // timing experiment: no staging
             if (kSrcU8)
                 stage_u8(in, xw, static_cast<const uint8_t*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_ROWS],
                          J[USDU_J_COLS], J[USDU_J_LEAD]);
@@ -381,8 +377,7 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
         });
         __syncthreads();
         if (first) tma::mbar_wait(bar, 0);     // the canvas block has landed
-        if (dbg & 4) {                         // timing experiment: no V pass
-        } else if (J[USDU_J_FLAGS] & 1) {
+        if (J[USDU_J_FLAGS] & 1) {
             BlendOpaque epi;
             epi.d = D;
             vpass_any(mid, rows_v, J, epi, 0, J[USDU_J_ROWS_OUT]);
@@ -446,8 +441,6 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
                  const uint8_t* mask_pool, const int32_t* items, int n_items, const int32_t* cover, int patch_w,
                  int patch_h, const void* src, int src_is_u8, int block_rows, cudaStream_t st) {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("USDU_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }   // profiling experiments only
     if (block_rows <= 0 || block_rows > FBH) {
         set_error("usdu_tile_blend: fast path needs the block height (1..%d) in flags bits 8..15, got %d", FBH, block_rows);
         return USDU_ERR_INVALID;
@@ -464,9 +457,9 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (src_is_u8)
-        USDU_CUDA(launch_pdl(blend_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap));
+        USDU_CUDA(launch_pdl(blend_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap));
     else
-        USDU_CUDA(launch_pdl(blend_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, dbg, cmap));
+        USDU_CUDA(launch_pdl(blend_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap));
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
