@@ -331,7 +331,7 @@ template <bool kSrcU8>
 __global__ void __launch_bounds__(kT, 4)
 blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool,
                   const int32_t* __restrict__ jobs, const void* __restrict__ src_v, int W3, int patch_w, int patch_h,
-                  int block_rows, const __grid_constant__ CUtensorMap cmap) {
+                  int block_rows, int remote, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     // [canvas block: 2 boxes x block_rows x 192] [job, rows_v] [bar] [in] [mid]
     const size_t dbytes = (size_t)2 * block_rows * kDBox;
@@ -398,7 +398,12 @@ blend_fast_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ 
         tma::store_3d(&cmap, bx3, by, b, smem);
         if (two) tma::store_3d(&cmap, bx3 + kDBox, by, b, smem + (size_t)block_rows * kDBox);
         tma::store_commit();
-        tma::store_wait_read();
+        if (remote) {                          // peer canvas: the writes must have landed before the grid can be
+            tma::store_wait_all();             // followed by a cross-GPU barrier
+            __threadfence_system();
+        } else {
+            tma::store_wait_read();
+        }
     }
 }
 
@@ -440,7 +445,7 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
 
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
                  const uint8_t* mask_pool, const int32_t* items, int n_items, const int32_t* cover, int patch_w,
-                 int patch_h, const void* src, int src_is_u8, int block_rows, cudaStream_t st) {
+                 int patch_h, const void* src, int src_is_u8, int block_rows, int remote, cudaStream_t st) {
     if (block_rows <= 0 || block_rows > FBH) {
         set_error("usdu_tile_blend: fast path needs the block height (1..%d) in flags bits 8..15, got %d", FBH, block_rows);
         return USDU_ERR_INVALID;
@@ -457,9 +462,9 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
     int s = optin(fn, smem);
     if (s != USDU_OK) return s;
     if (src_is_u8)
-        USDU_CUDA(launch_pdl(blend_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap));
+        USDU_CUDA(launch_pdl(blend_fast_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, remote, cmap));
     else
-        USDU_CUDA(launch_pdl(blend_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, cmap));
+        USDU_CUDA(launch_pdl(blend_fast_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, patch_h, block_rows, remote, cmap));
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

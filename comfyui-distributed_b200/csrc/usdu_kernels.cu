@@ -438,7 +438,7 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
                 const int32_t* items, int n_items, int patch_w, int patch_h, float* out, cudaStream_t st);
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tiles, const int32_t* tabs,
                  const uint8_t* mask_pool, const int32_t* items, int n_items, const int32_t* cover, int patch_w,
-                 int patch_h, const void* src, int src_is_u8, int block_rows, cudaStream_t st);
+                 int patch_h, const void* src, int src_is_u8, int block_rows, int remote, cudaStream_t st);
 } }
 
 using namespace usdu;
@@ -627,7 +627,8 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, con
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: fast path needs tables");
         USDU_REQUIRE(((uintptr_t)src_dev & 15) == 0, "usdu_tile_blend: src must be 16-byte aligned");
         return fast::launch_blend(canvas_dev, B, H, W, pitch, tiles_dev, tabs_dev, mask_pool_dev, items_dev, n_items,
-                                  cover_dev, patch_w, patch_h, src_dev, src_is_u8, (flags >> 8) & 0xFF, (cudaStream_t)stream);
+                                  cover_dev, patch_w, patch_h, src_dev, src_is_u8, (flags >> 8) & 0xFF,
+                                  (flags & USDU_FLAG_REMOTE_CANVAS) ? 1 : 0, (cudaStream_t)stream);
     }
     const int in_pitch = (patch_w * 3 + 15) / 16 * 16;
     const size_t smem = (size_t)BH * BW * 3 + (size_t)patch_h * BW * 3 + (size_t)patch_h * in_pitch;

@@ -82,6 +82,12 @@ def tile_payload_layout(plan, assignment: Sequence[Sequence[int]], B: int):
 import os
 
 USE_PEER_BLEND = os.environ.get("USDU_PEER_BLEND", "1") != "0"
+# ... and, with it, the final blend itself is shared out: the master's canvas is a symmetric
+# allocation too, every rank composites its share of the canvas BLOCKS (all worker tiles, ascending
+# id, same order inside every block) straight into the master's HBM, reading the tiles from their
+# owners' HBM.  Blocks are owned by exactly one CTA of exactly one rank, so the result is the one
+# the single launch on the master produces.
+USE_SHARED_FINAL_BLEND = os.environ.get("USDU_SHARED_FINAL_BLEND", "1") != "0"
 
 
 def peer_offsets(order: Sequence[int], where: Dict[int, Tuple[int, int]], ptrs: Sequence[int], own_rank: int) -> np.ndarray:
@@ -92,7 +98,7 @@ def peer_offsets(order: Sequence[int], where: Dict[int, Tuple[int, int]], ptrs: 
 
 
 class PeerPayload:
-    """Symmetric u8 buffer + rendezvous handle, cached per (bytes, device, group)."""
+    """Symmetric u8 buffer + rendezvous handle, cached per (tag, bytes, device, group)."""
 
     _cache: Dict[tuple, Optional["PeerPayload"]] = {}
 
@@ -110,12 +116,12 @@ class PeerPayload:
         self.hdl.barrier(channel=channel, timeout_ms=20000)
 
     @classmethod
-    def get(cls, nbytes: int, device, group) -> Optional["PeerPayload"]:
+    def get(cls, nbytes: int, device, group, tag: str = "payload") -> Optional["PeerPayload"]:
         """Collective.  Returns None on EVERY rank if any rank cannot set the buffer up (no
         NVLink/P2P, symmetric memory unsupported) -- the caller then uses the NCCL all-gather."""
         if not (USE_PEER_BLEND and td.is_initialized() and td.get_backend(group) == "nccl"):
             return None
-        key = (int(nbytes), str(device), id(group))
+        key = (tag, int(nbytes), str(device), id(group))
         if key in cls._cache:
             return cls._cache[key]
         obj, ok = None, 1
@@ -128,7 +134,7 @@ class PeerPayload:
         td.all_reduce(flag, op=td.ReduceOp.MIN, group=group)
         if int(flag.item()) == 0:
             obj = None
-        if len(cls._cache) > 4:
+        if len(cls._cache) > 8:
             cls._cache.clear()
         cls._cache[key] = obj
         return obj
@@ -174,14 +180,19 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
         payload = None
         peer = PeerPayload.get((max(sizes) + 255) // 256 * 256, image.device, group) if world > 1 else None
+        shared = None     # symmetric canvases: every rank can composite into the master's
+        if peer is not None and USE_SHARED_FINAL_BLEND and not all_ranks_result:
+            shared = PeerPayload.get(B * H * Canvas.pitch_of(W), image.device, group, tag="canvas")
+        cbuf = shared.buf.view(B, H, Canvas.pitch_of(W)) if shared is not None else None
         if world > 1:
             payload = (peer.buf[: sizes[rank]] if peer is not None
                        else _payload_buffer(sizes[rank], image.device))
         if graphed:      # this rank's wave loop (crop -> sampler -> local blend -> u8 pack) as one CUDA graph
-            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank], payload=payload, where=where)
+            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank], payload=payload, where=where,
+                                       canvas_buf=cbuf)
             canvas, base = gw.replay(image), None
         else:
-            canvas = Canvas(dp, B).load(image)
+            canvas = Canvas(dp, B, cbuf).load(image)
             base = canvas.clone() if (all_ranks_result and rank != 0) else None
             run_progressive(canvas, asg[rank], denoiser, payload=payload, where=where)
         if world > 1:
@@ -190,7 +201,12 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
             if produce_here and rank != 0:
                 # rebuild the master's canvas: base + master tiles in the master's order
                 target, order = base, list(asg[0]) + order
-            if peer is not None:
+            if shared is not None:
+                peer.barrier(0)                          # every payload is complete, the master's own tiles are blended
+                canvas.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank), part=(rank, world),
+                             canvas_ptr=shared.ptrs[0])
+                peer.barrier(1)                          # every share has landed in the master's canvas
+            elif peer is not None:
                 peer.barrier(0)                          # every payload is complete and visible
                 if produce_here:
                     target.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank))
@@ -212,6 +228,7 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         stats["tiles_this_rank"] = len(asg[rank])
         stats["conflict_free"] = plan.conflict_free(asg)
         stats["transport"] = "single" if world == 1 else ("nvlink peer loads" if peer is not None else "nccl all_gather")
+        stats["final_blend"] = "master" if shared is None else f"shared by {world} ranks (peer stores into the master's canvas)"
     return res
 
 

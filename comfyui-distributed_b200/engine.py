@@ -117,10 +117,11 @@ class DevicePlan:
             self._wl[key] = (wl, offs, total) + self._upload(wl)
         return self._wl[key]
 
-    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool, B: int = 1):
-        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast, B)
+    def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool, B: int = 1,
+                   part: Optional[Tuple[int, int]] = None):
+        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast, B, part)
         if key not in self._wl:
-            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast, B)
+            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast, B, part)
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
@@ -128,15 +129,23 @@ class DevicePlan:
 class Canvas:
     """The progressive u8 canvas [B, H, pitch] of one participant."""
 
-    def __init__(self, dplan: DevicePlan, B: int):
+    def __init__(self, dplan: DevicePlan, B: int, buf: Optional[torch.Tensor] = None):
         self.dp = dplan
         self.plan = dplan.plan
         self.B = B
-        self.pitch = (self.plan.W * 3 + 127) // 128 * 128
-        self.buf = torch.empty((B, self.plan.H, self.pitch), dtype=torch.uint8, device=dplan.device)
+        self.pitch = self.pitch_of(self.plan.W)
+        if buf is None:
+            buf = torch.empty((B, self.plan.H, self.pitch), dtype=torch.uint8, device=dplan.device)
+        elif tuple(buf.shape) != (B, self.plan.H, self.pitch) or buf.dtype != torch.uint8 or not buf.is_contiguous():
+            raise ValueError(f"canvas buffer must be contiguous uint8 [{B},{self.plan.H},{self.pitch}]")
+        self.buf = buf                      # caller-owned when given (dist.py: symmetric memory peers can address)
         self.launches = 0
         self.algo_bytes = 0
         self.flags = nat.FLAG_FAST if (self.plan.fast and not FORCE_GENERIC) else 0
+
+    @staticmethod
+    def pitch_of(W: int) -> int:
+        return (W * 3 + 127) // 128 * 128
 
     # Q0 (single_gpu.py:30-32)
     def load(self, image: torch.Tensor):
@@ -189,24 +198,30 @@ class Canvas:
         return out, offs
 
     # K4 (tile_ops.py:310-349 after the truncating cast of single_gpu.py:60)
-    def blend(self, tile_ids: Sequence[int], src: torch.Tensor, offs: np.ndarray):
+    def blend(self, tile_ids: Sequence[int], src: torch.Tensor, offs: np.ndarray,
+              part: Optional[Tuple[int, int]] = None, canvas_ptr: Optional[int] = None):
         """Composite processed tiles into the canvas in the ORDER of `tile_ids`.
-        src: flat fp32 (sampler output) or uint8 (already quantised) buffer."""
+        src: flat fp32 (sampler output) or uint8 (already quantised) buffer.
+        part = (i, n): this launch takes the i-th of n shares of the canvas blocks; canvas_ptr: device
+        address of ANOTHER participant's canvas of the same geometry (peer memory) to composite into."""
         _require_cuda(src, "src")
         tile_ids = tuple(int(t) for t in tile_ids)
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B)
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B, part)
         if items.shape[0] == 0:
             return
         p = self.plan
         src = src.contiguous()
         n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
         flags = self.flags | (wl.block_rows << 8) | (wl.block_cols << 16)
+        target = self.buf.data_ptr()
+        if canvas_ptr is not None and canvas_ptr != target:
+            target, flags = canvas_ptr, flags | nat.FLAG_REMOTE_CANVAS
         cover_ptr = cover.data_ptr() if cover is not None else 0
         _launch("blend", wl.algo_bytes * self.B,
-                lambda: nat.tile_blend(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
+                lambda: nat.tile_blend(target, self.B, p.H, p.W, self.pitch, self.dp.tiles.data_ptr(),
                                        self.dp.tabs.data_ptr(), self.dp.mask_pool.data_ptr(), items.data_ptr(),
                                        n_grid, cover_ptr, wl.patch_w, wl.patch_h, src.data_ptr(),
                                        src_u8, flags, _stream_ptr()))
@@ -319,9 +334,10 @@ class GraphedWaves:
 
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
                  order: Optional[Sequence[int]] = None, keep_processed: bool = False,
-                 payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()):
+                 payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = (),
+                 canvas_buf: Optional[torch.Tensor] = None):
         global PROFILE
-        self.canvas = Canvas(dp, B)
+        self.canvas = Canvas(dp, B, canvas_buf)
         self.denoiser = denoiser
         order = list(range(len(dp.plan.tiles))) if order is None else list(order)
         self.shipped: Dict[int, torch.Tensor] = {}
@@ -354,15 +370,18 @@ class GraphedWaves:
     @classmethod
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None,
             order: Optional[Sequence[int]] = None, keep_processed: bool = False,
-            payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()) -> "GraphedWaves":
+            payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = (),
+            canvas_buf: Optional[torch.Tensor] = None) -> "GraphedWaves":
         pkey = None if payload is None else (payload.data_ptr(), payload.numel())
+        ckey = None if canvas_buf is None else canvas_buf.data_ptr()
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC,
-               None if order is None else tuple(order), keep_processed, pkey, tuple(skip))
+               None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
             if len(cls._cache) > 6:
                 cls._cache.clear()
-            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip)
+            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip,
+                                                canvas_buf)
         return gw
 
     def replay(self, image: torch.Tensor) -> Canvas:

@@ -476,9 +476,11 @@ class Plan:
         return J
 
     def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
-                       use_fast: Optional[bool] = None, B: int = 1) -> WorkList:
+                       use_fast: Optional[bool] = None, B: int = 1, part: Optional[Tuple[int, int]] = None) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
-        given order (the order of `tile_ids` IS the blend order)."""
+        given order (the order of `tile_ids` IS the blend order).  part = (i, n): only the i-th of n
+        equal shares of the (sorted) block list -- every block is owned by exactly one CTA, so n
+        participants given the same tile list cover the launch disjointly (dist.upscale_static)."""
         use_fast = self.fast if use_fast is None else (use_fast and self.fast)
         ext = []
         for t in tile_ids:
@@ -510,6 +512,19 @@ class Plan:
         order = np.lexsort((seq, keys))             # by block, then by position in tile_ids
         keys, tids, seq = keys[order], tids[order], seq[order]
         first = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
+        if part is not None:
+            i, n = part
+            nb = int(first.size)
+            lo, hi = (nb * i) // n, (nb * (i + 1)) // n
+            a = int(first[lo]) if lo < nb else int(keys.size)
+            b = int(first[hi]) if hi < nb else int(keys.size)
+            nbytes = int(nbytes * (b - a) / max(int(keys.size), 1))
+            keys, tids, seq = keys[a:b], tids[a:b], seq[a:b]
+            if keys.size == 0:
+                return WorkList(np.zeros((0, nat.JOB_WORDS if use_fast else nat.BLEND_ITEM_WORDS), np.int32),
+                                None if use_fast else np.zeros((0, nat.COVER_WORDS), np.int32), pw_max, ph_max, 0,
+                                n_launch=0, block_rows=bh if use_fast else bh, block_cols=0 if use_fast else bw)
+            first = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
         counts = np.diff(np.r_[first, keys.size])
         items = np.zeros((first.size, nat.BLEND_ITEM_WORDS), dtype=np.int64)
         items[:, 0] = (keys[first] % nbx) * bw

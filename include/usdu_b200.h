@@ -193,6 +193,11 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
  * bits 8..15 (<= USDU_BLOCK_H), columns in bits 16..23 (<= USDU_BLOCK_W); 0 = the default block.
  * The planner shrinks blocks when an extreme down-scale would not fit shared memory. */
 #define USDU_FLAG_BLOCK_COLS(n) ((n) << 16)
+/* usdu_tile_blend: canvas_dev is ANOTHER device's memory mapped into this process (NVLink peer
+ * access); the kernel then waits for its bulk stores to complete, not only to be read, and issues
+ * a system-scope fence before a CTA exits (the multi-GPU final blend composites shares of the
+ * master's canvas from every rank, dist.upscale_static). */
+#define USDU_FLAG_REMOTE_CANVAS (1 << 24)
 /* Q0: canvas_u8[b][y][x*3+c] = (uint8)(255.f * img[b][y][x][c])   (utils/image.py:8-10)
  * pitch = bytes per canvas row (>= 3*W, multiple of 16); frame stride = H*pitch. */
 int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W,

@@ -50,7 +50,8 @@ CASES = [("noise", 1, 300, 420, 128, 16, 8), ("noise", 1, 1100, 1300, 256, 32, 8
 def _w_static(rank, world, case, transport):
     from comfyui_distributed_b200 import dist as udist, planner
     from comfyui_distributed_b200.denoise import T0Denoiser
-    udist.USE_PEER_BLEND = transport == "peer"
+    udist.USE_PEER_BLEND = transport != "nccl"
+    udist.USE_SHARED_FINAL_BLEND = transport == "peer_shared"
     kind, B, H, W, tile, pad, blur = case
     p = planner.get_plan(W, H, tile, tile, pad, blur, True)
     for job in range(3):                                       # later jobs replay the graphs and reuse the payload buffers
@@ -58,8 +59,9 @@ def _w_static(rank, world, case, transport):
         x = torch.from_numpy(img).cuda()
         st = {}
         out = udist.upscale_static(x, T0Denoiser(9, 0.5), tile, tile, pad, blur, True, stats=st)
-        if transport == "peer":                                # NVLink boxes: the master's blend kernel reads the peers' HBM
+        if transport != "nccl":                                # NVLink boxes: the blend kernel reads the peers' HBM
             assert st["transport"] == "nvlink peer loads", (st["transport"], udist.PeerPayload.last_error)
+            assert st["final_blend"].startswith("shared" if transport == "peer_shared" else "master"), st["final_blend"]
         else:
             assert st["transport"] == "nccl all_gather"
         if rank != 0:
@@ -70,7 +72,7 @@ def _w_static(rank, world, case, transport):
         assert st["tiles_this_rank"] == len(p.partition(world)[0])
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer_shared", "peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}_{c[3]}x{c[2]}_b{c[1]}")
 def test_static_mode_matches_replay_oracle(world, case, transport):

@@ -223,3 +223,47 @@ def test_image_batch_divider_matches_reference_chunking():
     assert len(outs) == 10 and [o.shape[0] for o in outs] == [3, 2, 2] + [0] * 7
     assert torch.equal(torch.cat(outs[:3]), x) and outs[0].data_ptr() == x.data_ptr()      # zero-copy views
     assert [o.shape[0] for o in node.divide_batch(x, 99)] == [1, 1, 1, 1, 1, 1, 1, 0, 0, 0]
+
+
+@pytest.mark.parametrize("use_fast", [True, False])
+def test_blend_worklist_shares_cover_the_launch_disjointly(use_fast):
+    """part=(i, n): n participants given the same tile list own disjoint sets of canvas blocks whose
+    union is the whole launch, with every block's tile list intact (dist.upscale_static shares the
+    final blend out like this)."""
+    p = planner.Plan.build(2048, 1536, 512, 512, 32, 8, True)
+    assert p.fast
+    tiles = [t for t in range(len(p.tiles)) if t % 3]
+    offs = np.arange(len(tiles), dtype=np.int64) * (1 << 20)
+    full = p.blend_worklist(tiles, offs, 1, use_fast)
+
+    def blocks(wl):
+        """{(block x, block y): [(tile-specific word, ...) per record in order]}"""
+        out = {}
+        if use_fast:
+            J = wl.items.reshape(-1, nat.JOB_WORDS)
+            n_heads = wl.n_launch
+            for h in range(n_heads):
+                key, chain, i = (int(J[h, nat.J_DST_X]), int(J[h, nat.J_DST_Y])), [], h
+                while i >= 0:
+                    chain.append((int(J[i, nat.J_SRC_A]), int(J[i, nat.J_SRC_B]), int(J[i, nat.J_OFF_LO])))
+                    i = int(J[i, nat.J_NEXT])
+                assert key not in out
+                out[key] = chain
+        else:
+            it, cv = wl.items.reshape(-1, nat.BLEND_ITEM_WORDS), wl.cover.reshape(-1, nat.COVER_WORDS)
+            for x, y, first, cnt in it:
+                out[(int(x), int(y))] = [tuple(int(v) for v in cv[j, :3]) for j in range(first, first + cnt)]
+        return out
+
+    want = blocks(full)
+    for n in (2, 3, 8):
+        got, sizes = {}, []
+        for i in range(n):
+            part = blocks(p.blend_worklist(tiles, offs, 1, use_fast, part=(i, n)))
+            assert not (set(part) & set(got))
+            got.update(part)
+            sizes.append(len(part))
+        assert got == want
+        assert max(sizes) - min(sizes) <= 1
+    empty = p.blend_worklist(tiles[:1], offs[:1], 1, use_fast, part=(63, 64))
+    assert empty.items.shape[0] in (0, empty.items.shape[0])          # tiny launches may leave a share empty
