@@ -2,7 +2,10 @@
 NVSwitch; gloo in the CPU tests).  Replaces the reference's HTTP + PNG transport:
 
 * upscale/worker_comms.py:16-108  (PNG multipart POST of processed tiles)  and
-  upscale/result_collector.py:36-182 (master drain loop)   -> all_gather of u8 tiles
+  upscale/result_collector.py:36-182 (master drain loop)   -> u8 tiles stay in their owner's HBM (symmetric
+                                                              memory); the blend kernels of all ranks read them
+                                                              over NVLink and composite shares of the master's
+                                                              canvas in place (fallback: all_gather of u8 tiles)
 * upscale/worker_comms.py:124-188 (HTTP pull of tile ids)  -> static plan (planner.partition)
 * nodes/collector.py:84-119 + api/job_routes.py:273-343 (base64 PNG per image)
                                                            -> all_gather of u8 images
