@@ -525,15 +525,19 @@ class HostPipeline:
         self.s_in.wait_stream(main)
         self.s_out.wait_stream(main)
 
+        # Rows y0:y1 of a multi-frame batch are B separate contiguous spans: one async copy per frame
+        # (a single strided copy_ would make torch stage the whole slab through pageable memory).
         def upload(band):
             y0, y1 = band["in"]
             src = host_in
             if stage is not None and y1 > y0:
-                stage[:, y0:y1].copy_(host_in[:, y0:y1])
+                for b in range(self.B):
+                    stage[b, y0:y1].copy_(host_in[b, y0:y1])
                 src = stage
             with torch.cuda.stream(self.s_in):
                 if y1 > y0:
-                    self.img[:, y0:y1].copy_(src[:, y0:y1], non_blocking=True)
+                    for b in range(self.B):
+                        self.img[b, y0:y1].copy_(src[b, y0:y1], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record()
             return e
@@ -550,7 +554,8 @@ class HostPipeline:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(e)
                 if f1 > f0:
-                    host_out[:, f0:f1].copy_(self.out[:, f0:f1], non_blocking=True)
+                    for b in range(self.B):
+                        host_out[b, f0:f1].copy_(self.out[b, f0:f1], non_blocking=True)
         main.wait_stream(self.s_out)
         main.wait_stream(self.s_in)
         return host_out
