@@ -8,6 +8,8 @@ Outputs (committed, small):
                                   the T0 denoiser (inputs are regenerated from seeds)
   tests/golden/prims.npz          create_tile_mask windows and blend_tile outputs
   tests/golden/mask_crop.npz      crop_mask outputs (conditioning masks cut to a tile), u8
+  tests/golden/static_ref_index.json   the reference's multi-worker static mode run over HTTP here: the tile
+                                  assignment each run ended up with + SHA-256 of the master's u8 result
 
 Test infrastructure only (see oracle/usdu_oracle.py header).
 """
@@ -30,7 +32,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
-from inputs import MASK_CROP_CASES, make_input, make_mask  # noqa: E402  (shared with the tests)
+from inputs import MASK_CROP_CASES, STATIC_REF_CASES, make_input, make_mask  # noqa: E402  (shared with the tests)
 
 
 def torch_t0(seed_unused=None):
@@ -100,11 +102,36 @@ def gen_mask_crop():
     np.savez_compressed(os.path.join(OUT, "mask_crop.npz"), **out)
 
 
+def gen_static_ref():
+    """tests/golden/static_ref_index.json: the reference's multi-worker static mode, really run (master +
+    workers over aiohttp with its PNG transport, oracle/ref_static_run.py): per case the tile assignment
+    that happened (the workers pull tile ids, so it is recorded, not chosen) and the SHA-256 of the
+    master's u8 result (the images are seeded noise -- incompressible -- so only the digest is stored)."""
+    import ref_static_run
+    index = []
+    for (name, kind, seed, B, H, W, tile, pad, blur, uni, n_workers, dseed, den) in STATIC_REF_CASES:
+        img = make_input(kind, seed, B, H, W)
+        res, asg = ref_static_run.run_static(img, n_workers, tile, pad, blur, uni, dseed, den, master_delay=0.25)
+        out = np.round(res * 255).astype(np.uint8)
+        assert np.array_equal(out.astype(np.float32) / np.float32(255), res)
+        replay = orc.replay_static(img, orc.make_t0_denoiser(dseed, den), tile, tile, pad, blur, uni, asg)
+        assert np.array_equal(replay, res), f"{name}: replay_static differs from the reference"
+        index.append({"name": name, "kind": kind, "seed": seed, "B": B, "H": H, "W": W, "tile": tile, "padding": pad,
+                      "mask_blur": blur, "uniform": uni, "denoise_seed": dseed, "denoise": den, "assignment": asg,
+                      "sha256": hashlib.sha256(out.tobytes()).hexdigest()})
+        print("static_ref", name, asg, index[-1]["sha256"][:16])
+    with open(os.path.join(OUT, "static_ref_index.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py (oracle/ref_static_run.py)", "reference": "a91f9fb", "cases": index}, f, indent=1)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--mask-crop-only" in sys.argv:
         return gen_mask_crop()
+    if "--static-ref-only" in sys.argv:
+        return gen_static_ref()
     gen_mask_crop()
+    gen_static_ref()
     node, fake_nodes = ref_loader.make_reference_node()
     fake_nodes.fn = torch_t0()
 

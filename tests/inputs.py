@@ -51,3 +51,13 @@ MASK_CROP_CASES = [
     ("mask_is_canvas", "blob", 7, 1, (1100, 1300), (0, 0, 544, 544), (1300, 1100), (544, 544)),
     ("upsample_tile", "noise", 8, 1, (90, 160), (992, 512, 1280, 800), (1280, 800), (544, 544)),
 ]
+
+
+# (name, kind, seed, B, H, W, tile, padding, blur, uniform, n_workers, denoise seed, denoise) -- multi-worker jobs run
+# through the REAL reference's HTTP static mode by oracle/gen_golden.py (oracle/ref_static_run.py)
+STATIC_REF_CASES = [
+    ("w1_700x520_t256", "noise", 3, 1, 520, 700, 256, 32, 8, True, 1, 9, 0.5),
+    ("w2_1300x1100_t512", "noise", 4, 1, 1100, 1300, 512, 32, 8, True, 2, 11, 0.5),
+    ("w1_b5_420x300_t128", "smooth", 5, 5, 300, 420, 128, 16, 8, True, 1, 13, 0.4),
+    ("w3_nonuniform_900x640_t256", "noise", 6, 1, 640, 900, 256, 16, 16, False, 3, 15, 0.6),
+]

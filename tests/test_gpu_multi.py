@@ -1,5 +1,6 @@
 """Multi-GPU (NCCL) parity: static mode across N ranks == oracle.replay_static with the
 same fixed partition; collector over NCCL == oracle.collector_combine.  Needs >= 2 GPUs."""
+import json
 import os
 import socket
 
@@ -79,6 +80,30 @@ def test_static_mode_matches_replay_oracle(world, case, transport):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     _run(_w_static, world, case, transport)
+
+
+def _w_recorded(rank, world, case):
+    import hashlib
+    from comfyui_distributed_b200 import dist as udist
+    from comfyui_distributed_b200.denoise import T0Denoiser
+    img = make_input(case["kind"], case["seed"], case["B"], case["H"], case["W"])
+    x = torch.from_numpy(img).cuda()
+    out = udist.upscale_static(x, T0Denoiser(case["denoise_seed"], case["denoise"]), case["tile"], case["tile"],
+                               case["padding"], case["mask_blur"], case["uniform"], assignment=case["assignment"])
+    if rank == 0:
+        q = np.round(out.cpu().numpy() * 255).astype(np.uint8)
+        assert hashlib.sha256(q.tobytes()).hexdigest() == case["sha256"]
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(os.path.dirname(__file__), "golden", "static_ref_index.json")))["cases"],
+                         ids=lambda c: c["name"])
+def test_static_mode_reproduces_the_real_reference_runs(case):
+    """The jobs the REAL reference ran over HTTP (tests/golden/static_ref_index.json: recorded pull-order
+    assignment + digest of the master's result) on as many ranks as that run had participants."""
+    world = len(case["assignment"])
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(_w_recorded, world, case)
 
 
 def _w_exact(rank, world, case):

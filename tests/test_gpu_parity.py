@@ -218,6 +218,42 @@ def test_static_replay_semantics_single_process():
     assert np.array_equal(master.result().cpu().numpy(), ref)
 
 
+STATIC_REF = json.load(open(os.path.join(G, "static_ref_index.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", STATIC_REF, ids=lambda c: c["name"])
+def test_static_jobs_of_the_real_reference_replayed_on_one_gpu(case):
+    """The multi-worker jobs the REAL reference ran over HTTP (oracle/ref_static_run.py; recorded pull
+    order, uniform and non-uniform tiles, B = 1 and 5) replayed participant by participant on one GPU:
+    per-participant progressive canvases in the recorded order, u8 transport, ascending final blend."""
+    import hashlib
+    B, H, W, tile = case["B"], case["H"], case["W"], case["tile"]
+    img = make_input(case["kind"], case["seed"], B, H, W)
+    p = planner.Plan.build(W, H, tile, tile, case["padding"], case["mask_blur"], case["uniform"])
+    den = T0Denoiser(case["denoise_seed"], case["denoise"])
+    dp = engine.DevicePlan.get(p, torch.device(DEV))
+    x = torch.from_numpy(img).to(DEV)
+    master, shipped = None, {}
+    for r, tiles in enumerate(case["assignment"]):
+        c = engine.Canvas(dp, B).load(x)
+        s = engine.run_progressive(c, tiles, den, keep_processed=True)
+        if r == 0:
+            master = c
+        else:
+            shipped.update(s)
+    order = sorted(shipped)
+    offs, cur = [], 0
+    for t in order:
+        offs.append(cur)
+        cur += (shipped[t].numel() + 15) // 16 * 16
+    src = torch.zeros(max(cur, 16), dtype=torch.uint8, device=DEV)
+    for t, o in zip(order, offs):
+        src[o:o + shipped[t].numel()] = shipped[t].reshape(-1)
+    master.blend(order, src, np.array(offs, dtype=np.int64))
+    out = master.result_u8().cpu().numpy()
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == case["sha256"]
+
+
 def test_full_size_properties_cfg2():
     """4K->8K canvas, 512-px tiles (BASELINE.json configs[1]) through size-independent
     properties: (i) denoise=0 with an identity sampler leaves every pixel whose crop was

@@ -57,3 +57,16 @@ def test_mask_crop_matches_reference():
         for b in range(B):
             got = orc.crop_mask_u8(orc.quantize_u8(m[b]), region, canvas, tile)
             assert np.array_equal(got, gold[name][b]), name
+
+
+STATIC_REF = json.load(open(os.path.join(G, "static_ref_index.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", STATIC_REF, ids=lambda c: c["name"])
+def test_replay_static_matches_the_reference_run_over_http(case):
+    """oracle.replay_static with the RECORDED tile assignment == what the reference's own static mode
+    (master + workers, aiohttp + PNG transport, really run by oracle/ref_static_run.py) produced."""
+    img = make_input(case["kind"], case["seed"], case["B"], case["H"], case["W"])
+    res = orc.replay_static(img, orc.make_t0_denoiser(case["denoise_seed"], case["denoise"]), case["tile"], case["tile"],
+                            case["padding"], case["mask_blur"], case["uniform"], case["assignment"])
+    assert hashlib.sha256(orc.quantize_u8(res).tobytes()).hexdigest() == case["sha256"]
