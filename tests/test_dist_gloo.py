@@ -58,9 +58,10 @@ def test_payload_layout_and_blend_order():
 
 
 def test_collector_order_matches_reference_rules():
-    # master first, then enabled order, duplicates once, unknown ids sorted last (collector.py:193-223)
+    # master first, then enabled order (an id listed twice contributes twice, as in the reference's loop --
+    # pinned against the real function by tests/test_collector_vs_reference.py), unknown ids sorted last
     ids = ["", "w_b", "w_a", "zz", "w_c"]
-    assert udist.collector_order(5, ["w_a", "w_b", "w_a", "w_x"], ids) == [0, 2, 1, 4, 3]
+    assert udist.collector_order(5, ["w_a", "w_b", "w_a", "w_x"], ids) == [0, 2, 1, 2, 4, 3]
     assert udist.collector_order(1, [], [""]) == [0]
 
 
