@@ -303,12 +303,15 @@ def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: i
 # --------------------------------------------------------------------------------------
 def collector_order(world: int, enabled_worker_ids: Sequence[str], worker_id_of_rank: Sequence[str]) -> List[int]:
     """Rank order of the collected batch: master (rank 0) first, then workers in the order of
-    `enabled_worker_ids` (an id listed twice contributes twice, exactly like the reference's loop),
-    then unexpected ids sorted (nodes/collector.py:193-223)."""
+    `enabled_worker_ids` with repeated ids dropped (the node de-duplicates the list before it assembles,
+    nodes/collector.py:245-253; the assembly loop itself, :193-223, would repeat them), then
+    unexpected ids sorted."""
     order = [0]
     rank_of = {str(w): r for r, w in enumerate(worker_id_of_rank) if r != 0}
     seen = set()
     for w in [str(x) for x in enabled_worker_ids]:
+        if w in seen:
+            continue
         seen.add(w)
         if w in rank_of:
             order.append(rank_of[w])

@@ -58,10 +58,11 @@ def test_payload_layout_and_blend_order():
 
 
 def test_collector_order_matches_reference_rules():
-    # master first, then enabled order (an id listed twice contributes twice, as in the reference's loop --
-    # pinned against the real function by tests/test_collector_vs_reference.py), unknown ids sorted last
+    # master first, then enabled order with repeated ids dropped (the node de-duplicates before assembling,
+    # collector.py:245-253; the raw assembly loop is pinned by tests/test_collector_vs_reference.py),
+    # unknown ids sorted last
     ids = ["", "w_b", "w_a", "zz", "w_c"]
-    assert udist.collector_order(5, ["w_a", "w_b", "w_a", "w_x"], ids) == [0, 2, 1, 2, 4, 3]
+    assert udist.collector_order(5, ["w_a", "w_b", "w_a", "w_x"], ids) == [0, 2, 1, 4, 3]
     assert udist.collector_order(1, [], [""]) == [0]
 
 
