@@ -563,10 +563,11 @@ class HostPipeline:
 
 class _PinnedPool:
     """Pinned result buffers, reused once the caller has dropped them.  A fresh 400 MB pinned
-    allocation costs ~17 ms (page locking) -- more than the whole pipelined job -- and torch's
+    allocation costs ~150 ms (page locking, measured) -- fifteen pipelined jobs -- and torch's
     host allocator does not hand a block back quickly enough when the previous result is still
-    referenced.  A buffer is recycled only if nothing but the pool references the tensor object
-    (views and numpy arrays keep their base alive, so they count)."""
+    referenced.  A buffer is recycled only if nothing but the pool references it: no other Python
+    reference to the tensor object (views hold one through `_base`) and no other owner of its storage
+    (numpy arrays made with `.numpy()` and views own the storage without referencing the tensor)."""
 
     def __init__(self, keep: int = 3):
         self.bufs: Dict[tuple, list] = {}
@@ -577,7 +578,8 @@ class _PinnedPool:
         key = (tuple(shape), dtype)
         lst = self.bufs.setdefault(key, [])
         for i in range(len(lst)):
-            if sys.getrefcount(lst[i]) <= 2:         # the list + getrefcount's own argument
+            # the list + getrefcount's own argument; the tensor + the temporary storage wrapper
+            if sys.getrefcount(lst[i]) <= 2 and torch._C._storage_Use_Count(lst[i].untyped_storage()._cdata) <= 2:
                 return lst[i]
         if len(lst) >= self.keep:
             lst.pop(0)                               # still referenced elsewhere: just forget it

@@ -6,6 +6,7 @@ import os
 import re
 
 import numpy as np
+import torch
 import pytest
 
 import usdu_oracle as orc
@@ -267,3 +268,35 @@ def test_blend_worklist_shares_cover_the_launch_disjointly(use_fast):
         assert max(sizes) - min(sizes) <= 1
     empty = p.blend_worklist(tiles[:1], offs[:1], 1, use_fast, part=(63, 64))
     assert empty.items.shape[0] in (0, empty.items.shape[0])          # tiny launches may leave a share empty
+
+
+def test_pinned_pool_never_recycles_a_buffer_somebody_still_sees():
+    """engine._PinnedPool hands a result buffer out again only when neither the tensor, nor a view, nor
+    a numpy array made from it is alive (page-locked memory is replaced by ordinary memory here)."""
+    from comfyui_distributed_b200 import engine
+
+    class Pool(engine._PinnedPool):
+        def get(self, shape, dtype=torch.float32):
+            import unittest.mock as um
+            real_empty = torch.empty
+            with um.patch.object(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"})):
+                return super().get(shape, dtype)
+
+    pool = Pool(keep=3)
+    a = pool.get((4, 8))
+    pa = a.data_ptr()
+    assert pool.get((4, 8)).data_ptr() != pa          # `a` is alive
+    del a
+    b = pool.get((4, 8))
+    assert b.data_ptr() == pa                          # dropped -> recycled
+    v = b[1]
+    del b
+    assert pool.get((4, 8)).data_ptr() != pa          # a view is alive
+    del v
+    c = pool.get((4, 8))
+    n = c.numpy()
+    pc = c.data_ptr()
+    del c
+    assert pool.get((4, 8)).data_ptr() != pc          # a numpy array is alive
+    del n
+    assert pool.get((4, 8)).data_ptr() in (pa, pc)
