@@ -32,7 +32,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
-from inputs import MASK_CROP_CASES, STATIC_REF_CASES, make_input, make_mask  # noqa: E402  (shared with the tests)
+from inputs import MASK_CROP_CASES, STATIC_REF_CASES, make_input, make_mask, sweep_cases, sweep_sampler  # noqa: E402  (shared with the tests)
 
 
 def torch_t0(seed_unused=None):
@@ -124,14 +124,37 @@ def gen_static_ref():
         json.dump({"generator": "oracle/gen_golden.py (oracle/ref_static_run.py)", "reference": "a91f9fb", "cases": index}, f, indent=1)
 
 
+def gen_sweep_digests():
+    """tests/golden/sweep_ref_digests.json: SHA-256 of the REAL reference's process_single_gpu output (u8) for
+    every case of the seeded parameter sweep the GPU tests run (tests/inputs.py sweep_cases)."""
+    node, fake_nodes = ref_loader.make_reference_node()
+    digests = {}
+    for (i, kind, B, H, W, tw, th, pad, blur, uni) in sweep_cases():
+        seed, den = sweep_sampler(i)
+        fake_nodes.fn = torch_t0()
+        img = make_input(kind, i, B, H, W)
+        (res,) = node.process_single_gpu(torch.from_numpy(img), None, [[torch.zeros(1, 77, 8), {}]],
+                                         [[torch.zeros(1, 77, 8), {}]], None, seed, 20, 8.0, "euler", "normal", den,
+                                         tw, th, pad, blur, uni, False)
+        out = np.round(res.numpy() * 255).astype(np.uint8)
+        assert np.array_equal(out.astype(np.float32) / np.float32(255), res.numpy())
+        digests[str(i)] = hashlib.sha256(out.tobytes()).hexdigest()
+        print("sweep", i, kind, B, H, W, tw, th, pad, blur, uni, digests[str(i)][:16], flush=True)
+    with open(os.path.join(OUT, "sweep_ref_digests.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py", "reference": "a91f9fb", "digests": digests}, f, indent=1)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--sweep-only" in sys.argv:
+        return gen_sweep_digests()
     if "--mask-crop-only" in sys.argv:
         return gen_mask_crop()
     if "--static-ref-only" in sys.argv:
         return gen_static_ref()
     gen_mask_crop()
     gen_static_ref()
+    gen_sweep_digests()
     node, fake_nodes = ref_loader.make_reference_node()
     fake_nodes.fn = torch_t0()
 

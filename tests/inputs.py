@@ -61,3 +61,32 @@ STATIC_REF_CASES = [
     ("w1_b5_420x300_t128", "smooth", 5, 5, 300, 420, 128, 16, 8, True, 1, 13, 0.4),
     ("w3_nonuniform_900x640_t256", "noise", 6, 1, 640, 900, 256, 16, 16, False, 3, 15, 0.6),
 ]
+
+
+def sweep_cases():
+    """Seeded sweep over the node's parameter space on small canvases (tests/test_gpu_sweep.py; the real
+    reference's digests for the same cases: tests/golden/sweep_ref_digests.json by oracle/gen_golden.py).
+    -> (id, kind, B, H, W, tile_w, tile_h, padding, mask_blur, uniform); input seed = id, T0 seed = 1000 + id,
+    denoise = 0.25 + 0.05 * (id % 10)."""
+    rng = np.random.default_rng(20260921)
+    out = []
+    for i in range(40):
+        W = int(rng.integers(24, 700))
+        H = int(rng.integers(24, 500))
+        tw = int(rng.choice([64, 72, 96, 128, 200, 256, 512]))
+        th = int(rng.choice([64, 80, 128, 256, 384]))
+        pad = int(rng.choice([0, 8, 16, 32, 64, 128]))
+        blur = int(rng.choice([0, 1, 4, 8, 16, 40, 97]))
+        uniform = bool(rng.integers(0, 2))
+        B = int(rng.choice([1, 1, 1, 2, 5]))
+        kind = ["noise", "smooth", "checker"][int(rng.integers(0, 3))]
+        out.append((i, kind, B, H, W, tw, th, pad, blur, uniform))
+    out += [(100, "noise", 1, 64, 48, 512, 512, 32, 8, True),      # canvas << tile: 544 -> 48 needs 68 taps (generic kernels)
+            (101, "noise", 1, 37, 1021, 64, 64, 8, 8, True),       # odd width, wide and flat
+            (102, "checker", 1, 515, 33, 128, 128, 16, 255, True),  # narrow, blur far larger than the canvas
+            (103, "smooth", 17, 96, 120, 64, 64, 16, 8, True)]      # WAN-style 4n+1 frame batch
+    return out
+
+
+def sweep_sampler(i: int):
+    return 1000 + i, 0.25 + 0.05 * (i % 10)

@@ -70,3 +70,21 @@ def test_replay_static_matches_the_reference_run_over_http(case):
     res = orc.replay_static(img, orc.make_t0_denoiser(case["denoise_seed"], case["denoise"]), case["tile"], case["tile"],
                             case["padding"], case["mask_blur"], case["uniform"], case["assignment"])
     assert hashlib.sha256(orc.quantize_u8(res).tobytes()).hexdigest() == case["sha256"]
+
+
+SWEEP_DIGESTS = json.load(open(os.path.join(G, "sweep_ref_digests.json")))["digests"]
+
+
+def _sweep_subset():
+    from inputs import sweep_cases
+    cs = sweep_cases()
+    return cs[::3] + cs[-4:]          # every third case + the four hand-picked extremes (all 44 run on the GPU box)
+
+
+@pytest.mark.parametrize("case", _sweep_subset(), ids=lambda c: f"{c[0]}-{c[1]}-b{c[2]}-{c[4]}x{c[3]}")
+def test_oracle_matches_reference_digests_of_the_parameter_sweep(case):
+    from inputs import sweep_sampler
+    i, kind, B, H, W, tw, th, pad, blur, uniform = case
+    seed, den = sweep_sampler(i)
+    res = orc.process_single(make_input(kind, i, B, H, W), orc.make_t0_denoiser(seed, den), tw, th, pad, blur, uniform)
+    assert hashlib.sha256(orc.quantize_u8(res).tobytes()).hexdigest() == SWEEP_DIGESTS[str(i)]
