@@ -103,7 +103,8 @@ class ComfySampler:
         import nodes as comfy_nodes  # ComfyUI's module; raises ImportError outside ComfyUI
         self.n = comfy_nodes
         self.args = (model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler, denoise)
-        self.tiled_decode = tiled_decode and hasattr(comfy_nodes, "VAEDecodeTiled")
+        # both tiled classes must import, like upscale/tile_ops.py:249-254 (the encode stays non-tiled, :276)
+        self.tiled_decode = tiled_decode and hasattr(comfy_nodes, "VAEDecodeTiled") and hasattr(comfy_nodes, "VAEEncodeTiled")
         self.image_size = image_size
         self.cond_cropper = cond_cropper
         try:        # user cancel is polled once per tile like upscale/modes/static.py:326,407,476
