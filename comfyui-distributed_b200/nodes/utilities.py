@@ -19,11 +19,22 @@ def chunk_bounds(total_items: int, n_splits: int):
     return out
 
 
+class _Wildcard(str):
+    """ComfyUI's link validation compares types with `!=`; a type that is never unequal connects to
+    anything (the reference's AnyType, nodes/utilities.py:79-83)."""
+
+    def __ne__(self, other) -> bool:
+        return False
+
+
 class _AnyTuple(tuple):
-    """ComfyUI indexes RETURN_TYPES per connected output; every slot is an IMAGE."""
+    """ComfyUI indexes RETURN_TYPES per connected output: every index answers with the wildcard type,
+    like the reference's ByPassTypeTuple (nodes/utilities.py:226-233); iteration still yields the
+    declared entries."""
 
     def __getitem__(self, index):
-        return "IMAGE" if isinstance(index, int) and index >= len(self) else super().__getitem__(index)
+        item = super().__getitem__(0 if isinstance(index, int) and index > 0 else index)
+        return _Wildcard("*") if isinstance(item, str) else item
 
 
 class ImageBatchDivider:
@@ -36,7 +47,7 @@ class ImageBatchDivider:
         }}
 
     RETURN_TYPES = _AnyTuple(("IMAGE",))
-    RETURN_NAMES = tuple(f"batch_{i + 1}" for i in range(MAX_PARTS))
+    RETURN_NAMES = _AnyTuple(tuple(f"batch_{i + 1}" for i in range(MAX_PARTS)))
     FUNCTION = "divide_batch"
     OUTPUT_NODE = True
     CATEGORY = "image"
