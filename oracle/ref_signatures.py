@@ -56,7 +56,19 @@ def reference_signatures() -> dict:
         # the sampler / scheduler lists come from ComfyUI (stubbed here): compare their position only
         up["input_types"]["required"]["sampler_name"] = ["<comfy.samplers.KSampler.SAMPLERS>"]
         up["input_types"]["required"]["scheduler"] = ["<comfy.samplers.KSampler.SCHEDULERS>"]
-        out = {"UltimateSDUpscaleDistributed": up,
+        import torch
+        errors = {}
+        node = up_mod.UltimateSDUpscaleDistributed()
+        base = (None, None, None, None, 0, 20, 8.0, "euler", "normal", 0.5, 64, 64, 8, 8, True, False)
+        try:
+            node.run(torch.zeros(2, 64, 64, 3), *base)
+        except Exception as e:      # noqa: BLE001
+            errors["batch_of_2_master"] = [type(e).__name__, str(e)]
+        try:
+            node.run(torch.zeros(1, 64, 64, 3), *base, multi_job_id="j", is_worker=False, enabled_worker_ids="[not json")
+        except Exception as e:      # noqa: BLE001
+            errors["malformed_enabled_worker_ids"] = [type(e).__name__]
+        out = {"UltimateSDUpscaleDistributed": up, "errors": errors,
                "upscale_mappings": {"NODE_CLASS_MAPPINGS": sorted(up_mod.NODE_CLASS_MAPPINGS),
                                     "NODE_DISPLAY_NAME_MAPPINGS": dict(up_mod.NODE_DISPLAY_NAME_MAPPINGS)}}
     finally:

@@ -49,3 +49,26 @@ def test_divider_outputs_are_wildcards_like_the_reference():
     rt = our_nodes.ImageBatchDivider.RETURN_TYPES
     assert not (rt[0] != "IMAGE") and not (rt[7] != "MASK") and rt[3] == "*"      # never unequal to any type
     assert tuple(rt) == ("IMAGE",) and len(tuple(our_nodes.ImageBatchDivider.RETURN_NAMES)) == 10
+
+
+def test_error_behaviour_equals_reference():
+    """Same exception types (and the same message for the batch rule) as the reference's run(), raised
+    before any device work (so this runs without a GPU)."""
+    import torch
+    from comfyui_distributed_b200.testing import T0Model
+    want = GOLD["errors"]
+    node = our_nodes.UltimateSDUpscaleDistributed()
+    base = (T0Model(), None, None, None, 0, 20, 8.0, "euler", "normal", 0.5, 64, 64, 8, 8, True, False)
+    with pytest.raises(ValueError) as e:
+        node.run(torch.zeros(2, 64, 64, 3), *base)
+    assert [type(e.value).__name__, str(e.value)] == want["batch_of_2_master"]
+    with pytest.raises(json.JSONDecodeError) as e:
+        node.run(torch.zeros(1, 64, 64, 3), *base, multi_job_id="j", is_worker=False, enabled_worker_ids="[not json")
+    assert type(e.value).__name__ == want["malformed_enabled_worker_ids"][0]
+    # the batch rule is the master's only (nodes/distributed_upscale.py:137): a worker with B = 2 gets past it
+    try:
+        node.run(torch.zeros(2, 64, 64, 3), *base, is_worker=True)
+    except ValueError as err:                      # pragma: no cover
+        assert "4n+1" not in str(err)
+    except Exception:                              # no GPU here: NativeError / CUDA error further down is fine
+        pass
