@@ -180,7 +180,8 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
         proc = [_eng.processing_order(plan, a) for a in asg]
         where, sizes = tile_payload_layout(plan, proc, B)
         sizes = [max(sz, 16) for sz in sizes]
-        graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
+        graphed = (bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
+                   and len(asg[rank]) > 0)          # a participant without tiles has nothing to capture
         payload = None
         peer = PeerPayload.get((max(sizes) + 255) // 256 * 256, image.device, group) if world > 1 else None
         shared = None     # symmetric canvases: every rank can composite into the master's
