@@ -422,6 +422,30 @@ def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, til
 # --------------------------------------------------------------------------------------
 # host-tensor path: H2D, compute and D2H overlapped band by band
 # --------------------------------------------------------------------------------------
+def host_bands(plan: Plan, n_bands: int) -> List[dict]:
+    """Bands of whole tile rows for the host pipeline.  Per band: `tiles` (row-major ids; processed in
+    wave order inside the band), `in` = [lo, hi) image rows that have to be on the device before the band
+    starts (everything up to its lowest crop window; consecutive bands continue where the previous one
+    stopped, the last one takes the rest), `fin` = [lo, hi) canvas rows that are final once the band is
+    done (no later band's feather support reaches them) and can travel back to the host."""
+    rows = sorted({t.y for t in plan.tiles})
+    n_bands = max(1, min(n_bands, len(rows)))
+    cuts = [round(i * len(rows) / n_bands) for i in range(n_bands + 1)]
+    bands = []
+    fin_lo = in_lo = 0
+    for k in range(n_bands):
+        ys = set(rows[cuts[k]:cuts[k + 1]])
+        tiles = [t.idx for t in plan.tiles if t.y in ys]
+        later = [t for t in plan.tiles if t.y > max(ys)]
+        in_hi = max(plan.tiles[i].y2 for i in tiles)
+        fin_hi = min((t.y1 + plan.support(t)[1] for t in later), default=plan.H)
+        fin_hi = max(fin_hi, fin_lo)
+        bands.append({"tiles": tiles, "in": (in_lo, max(in_hi, in_lo)), "fin": (fin_lo, fin_hi)})
+        in_lo, fin_lo = max(in_hi, in_lo), fin_hi
+    bands[-1]["in"] = (bands[-1]["in"][0], plan.H)
+    return bands
+
+
 class HostPipeline:
     """One-GPU job for a HOST image (what ComfyUI hands a node), pipelined over bands of tile
     rows so that PCIe traffic in both directions overlaps with itself and with the kernels.
@@ -443,21 +467,8 @@ class HostPipeline:
         self.canvas = Canvas(dp, B)
         self.img = torch.empty((B, plan.H, plan.W, 3), dtype=torch.float32, device=dev)
         self.out = torch.empty((B, plan.H, plan.W, 3), dtype=torch.float32, device=dev)
-        rows = sorted({t.y for t in plan.tiles})
-        n_bands = max(1, min(n_bands, len(rows)))
-        cuts = [round(i * len(rows) / n_bands) for i in range(n_bands + 1)]
-        self.bands = []
-        fin_lo = in_lo = 0
-        for k in range(n_bands):
-            ys = set(rows[cuts[k]:cuts[k + 1]])
-            tiles = [t.idx for t in plan.tiles if t.y in ys]
-            later = [t for t in plan.tiles if t.y > max(ys)]
-            in_hi = max(plan.tiles[i].y2 for i in tiles)
-            fin_hi = min((t.y1 + plan.support(t)[1] for t in later), default=plan.H)
-            fin_hi = max(fin_hi, fin_lo)
-            self.bands.append({"tiles": tiles, "in": (in_lo, max(in_hi, in_lo)), "fin": (fin_lo, fin_hi)})
-            in_lo, fin_lo = max(in_hi, in_lo), fin_hi
-        self.bands[-1]["in"] = (self.bands[-1]["in"][0], plan.H)
+        self.bands = host_bands(plan, n_bands)
+        n_bands = len(self.bands)
         self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self.graph_safe = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
         self.graphs = [None] * n_bands

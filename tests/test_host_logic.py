@@ -300,3 +300,34 @@ def test_pinned_pool_never_recycles_a_buffer_somebody_still_sees():
     assert pool.get((4, 8)).data_ptr() != pc          # a numpy array is alive
     del n
     assert pool.get((4, 8)).data_ptr() in (pa, pc)
+
+
+@pytest.mark.parametrize("W,H,tile,pad,blur,uniform", [(7680, 4320, 512, 32, 8, True), (1300, 1100, 256, 32, 16, True),
+                                                        (700, 520, 256, 32, 8, False), (333, 777, 64, 128, 40, True),
+                                                        (3840, 2160, 512, 32, 8, True), (100, 90, 128, 32, 8, True)])
+def test_host_pipeline_bands_are_a_safe_schedule(W, H, tile, pad, blur, uniform):
+    """engine.host_bands: the band-by-band order is a topological order of the progressive DAG, a band
+    never crops rows that have not been uploaded yet, and rows declared final are never written again."""
+    from comfyui_distributed_b200.engine import host_bands
+    p = planner.Plan.build(W, H, tile, tile, pad, blur, uniform)
+    n_rows = len({t.y for t in p.tiles})
+    for n_bands in sorted({1, 2, 3, n_rows, n_rows + 5}):
+        bands = host_bands(p, n_bands)
+        assert 1 <= len(bands) <= min(n_bands, n_rows)
+        order = [t for b in bands for w in p.waves(b["tiles"]) for t in w]
+        assert sorted(order) == list(range(len(p.tiles)))
+        pos = {t: i for i, t in enumerate(order)}
+        for t in range(len(p.tiles)):                  # every earlier overlapping tile of the row-major order comes first
+            assert all(pos[n] < pos[t] for n in p.neighbors[t] if n < t), (n_bands, t)
+        in_end = fin_end = 0
+        for k, b in enumerate(bands):
+            assert b["in"][0] == in_end and b["in"][1] >= b["in"][0]
+            in_end = b["in"][1]
+            assert max(p.tiles[t].y2 for t in b["tiles"]) <= in_end          # crops read uploaded rows only
+            assert b["fin"][0] == fin_end and b["fin"][1] >= b["fin"][0]
+            fin_end = b["fin"][1]
+            later = [t for bb in bands[k + 1:] for t in bb["tiles"]]
+            for t in later:                                                     # nobody writes below fin_end any more
+                assert p.tiles[t].y1 + p.support(p.tiles[t])[1] >= fin_end
+            assert fin_end <= in_end
+        assert in_end == H and fin_end == H
