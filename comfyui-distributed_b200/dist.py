@@ -17,6 +17,7 @@ canvas with every worker tile blended on top in ascending tile id
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -82,8 +83,6 @@ def tile_payload_layout(plan, assignment: Sequence[Sequence[int]], B: int):
 # unified virtual address space a tile of rank r is simply  own_base + (ptr[r] - ptr[own]) +
 # offset, which the blend kernel's 64-bit source offsets already express.
 # --------------------------------------------------------------------------------------
-import os
-
 USE_PEER_BLEND = os.environ.get("USDU_PEER_BLEND", "1") != "0"
 # ... and, with it, the final blend itself is shared out: the master's canvas is a symmetric
 # allocation too, every rank composites its share of the canvas BLOCKS (all worker tiles, ascending
