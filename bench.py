@@ -243,7 +243,8 @@ def main():
     clocks.start()
     stats = {}
     ms_step = timed(lambda: step_device(stats), args.steps)
-    clk = clocks.stop()
+    # (the sampler keeps running through the per-kernel and end-to-end timed loops below: K steps of a
+    # 1.3 ms job are over before nvidia-smi's first 100 ms tick)
     stats["gpu_launches"] = stats.get("gpu_launches", 0) // args.steps        # per step
     stats["algo_bytes"] = stats.get("algo_bytes", 0) // args.steps
 
@@ -301,6 +302,7 @@ def main():
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    clk = clocks.stop()
     img_bytes = B * H * W * 3 * 4
 
     # ---- supplementary: the same job with an SDXL-cost sampler (T1), one timed step -----------
