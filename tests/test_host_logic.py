@@ -331,3 +331,25 @@ def test_host_pipeline_bands_are_a_safe_schedule(W, H, tile, pad, blur, uniform)
                 assert p.tiles[t].y1 + p.support(p.tiles[t])[1] >= fin_end
             assert fin_end <= in_end
         assert in_end == H and fin_end == H
+
+
+def test_table_builders_fuzz_against_oracle():
+    """300 random (filter, in, out) axes: the C builders' bounds / coefficients / input spans and the
+    NEAREST index arithmetic equal the oracle's restatement of Pillow bit for bit."""
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        filt = int(rng.integers(0, 2))
+        n_in, n_out = int(rng.integers(1, 900)), int(rng.integers(1, 900))
+        if n_in / n_out > 40:                 # keep ksize (and the test) small
+            continue
+        tab = nat.build_filter_table(filt, n_in, n_out)
+        bounds, kk = orc.resample_coeffs(n_in, n_out, ("lanczos", "bicubic")[filt])
+        H = nat.TAB_HEADER
+        assert tab[2] == kk.shape[1]
+        assert np.array_equal(tab[H:H + 2 * n_out].reshape(n_out, 2), bounds)
+        assert np.array_equal(tab[H + 2 * n_out:].reshape(n_out, kk.shape[1]), kk)
+        a = int(rng.integers(0, n_out))
+        n = int(rng.integers(1, n_out - a + 1))
+        lo, cnt = nat.table_input_span(tab, a, n)
+        assert lo == bounds[a:a + n, 0].min() and lo + cnt == (bounds[a:a + n, 0] + bounds[a:a + n, 1]).max()
+        assert np.array_equal(nat.nearest_index(n_in, n_out), orc.nearest_index(n_in, n_out))
