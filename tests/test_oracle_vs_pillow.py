@@ -78,3 +78,26 @@ def test_composite_matches_pillow_blend_sequence():
 def test_quantize_round_trip_all_codes():
     u = np.arange(256, dtype=np.uint8)
     assert np.array_equal(orc.quantize_u8(orc.dequantize_u8(u)), u)
+
+
+@pytest.mark.parametrize("w,h,ow,oh", [(64, 48, 300, 200), (300, 200, 64, 48), (128, 128, 960, 540), (97, 31, 101, 77),
+                                       (540, 960, 135, 240), (33, 33, 33, 70)])
+def test_bicubic_resize_mode_L_matches_pillow(w, h, ow, oh):
+    """Image.resize(..., BICUBIC) on mode L: what crop_mask applies to conditioning masks
+    (utils/usdu_utils.py:424,435)."""
+    rng = np.random.default_rng(w * 1000 + h)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ref = np.array(Image.fromarray(a).resize((ow, oh), Image.Resampling.BICUBIC))
+    assert np.array_equal(orc.resize_u8(a, ow, oh, "bicubic"), ref)
+    ref = np.array(Image.fromarray(a).resize((ow, oh), Image.Resampling.LANCZOS))
+    assert np.array_equal(orc.resize_u8(a, ow, oh, "lanczos"), ref)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(5, 17), (542, 576), (30, 7), (100, 100), (3, 1000), (1, 9), (254, 255), (255, 254)])
+def test_nearest_index_matches_pillow(n_in, n_out):
+    """Image.resize(..., NEAREST) along one axis (pad_image2's edge strips, utils/usdu_utils.py:190-199)."""
+    a = (np.arange(n_in) % 251).astype(np.uint8)[None, :]
+    ref = np.array(Image.fromarray(a).resize((n_out, 1), Image.Resampling.NEAREST))[0]
+    assert np.array_equal(a[0][orc.nearest_index(n_in, n_out)], ref)
+    ref = np.array(Image.fromarray(a.T.copy()).resize((1, n_out), Image.Resampling.NEAREST))[:, 0]
+    assert np.array_equal(a[0][orc.nearest_index(n_in, n_out)], ref)
