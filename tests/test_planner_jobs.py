@@ -11,6 +11,7 @@ from __graft_entry__ import load_package
 from inputs import make_input
 
 load_package()
+from comfyui_distributed_b200 import _native as nat  # noqa: E402
 from comfyui_distributed_b200 import planner  # noqa: E402
 
 CASES = [("noise", 1, 300, 420, 128, 16, 8, True), ("smooth", 2, 260, 300, 128, 32, 16, True),
@@ -76,3 +77,67 @@ def test_blend_records_reproduce_ordered_blend(case, src_u8):
     for wave in p.waves():
         km.run_blend(p, got, p.blend_worklist(wave, np.array([offs[pos[t]] for t in wave]), 1 if src_u8 else 4, True, B), feed, pool)
     assert np.array_equal(got, want)
+
+
+GENERIC = [(48, 64, 512, 32, 8, True), (1021, 37, 64, 8, 8, True), (33, 515, 128, 16, 255, True), (300, 260, 128, 16, 16, False),
+           (2304, 96, 1152, 0, 4, True)]
+
+
+@pytest.mark.parametrize("W,H,tile,pad,blur,uniform", GENERIC)
+def test_generic_work_items_cover_every_output_once_and_fit_the_declared_patch(W, H, tile, pad, blur, uniform):
+    """The any-scale kernels compute their input windows from the tables themselves; the planner's part is
+    the item lists and the shared-memory capacity it declares (patch_w x patch_h).  Crop: the blocks tile
+    every output pixel of every tile exactly once and no block needs more input than declared.  Blend: every
+    canvas block appears once, lists exactly the tiles whose feather support touches it, in blend order,
+    and no (block, tile) pair needs more of the processed tile than declared."""
+    p = planner.Plan.build(W, H, tile, tile, pad, blur, uniform)
+    ids = list(range(len(p.tiles)))
+    H_ = nat.TAB_HEADER
+
+    def span(n_in, n_out, o0, cnt):
+        if n_in == n_out:
+            return o0, o0 + cnt
+        off = p._tab_off[(n_in, n_out)]
+        b = p.tabs[off + H_: off + H_ + 2 * n_out].reshape(n_out, 2)
+        return int(b[o0, 0]), int(b[o0 + cnt - 1, 0] + b[o0 + cnt - 1, 1])
+
+    wl, offs, total = p.crop_worklist(ids, 1, False)
+    bw, bh = wl.block_cols, wl.block_rows
+    hit = {t: np.zeros((p.tiles[t].ph, p.tiles[t].pw), dtype=np.int32) for t in ids}
+    for tid, ox0, oy0, off_lo, off_hi, rows in wl.items.reshape(-1, nat.CROP_ITEM_WORDS).tolist():
+        t = p.tiles[tid]
+        ow, oh = min(bw, t.pw - ox0), min(rows, t.ph - oy0)
+        assert ow > 0 and oh > 0 and rows <= bh
+        hit[tid][oy0:oy0 + oh, ox0:ox0 + ow] += 1
+        lo, hi = span(t.ew, t.pw, ox0, ow)
+        assert hi - lo <= wl.patch_w, ("crop", tid, hi - lo, wl.patch_w)
+        lo, hi = span(t.eh, t.ph, oy0, oh)
+        assert hi - lo <= wl.patch_h
+        assert (off_lo & 0xFFFFFFFF) | (off_hi << 32) == offs[ids.index(tid)]
+    assert all((h == 1).all() for h in hit.values())
+
+    boffs, _ = p.slot_offsets(ids, 1)
+    wl = p.blend_worklist(ids, boffs, 4, False, 1)
+    bw, bh = wl.block_cols, wl.block_rows
+    items, cover = wl.items.reshape(-1, nat.BLEND_ITEM_WORDS), wl.cover.reshape(-1, nat.COVER_WORDS)
+    seen = set()
+    for bx, by, first, count in items.tolist():
+        assert (bx, by) not in seen and bx % bw == 0 and by % bh == 0
+        seen.add((bx, by))
+        listed = [int(cover[j, 0]) for j in range(first, first + count)]
+        assert listed == sorted(listed)                                   # blend order of this launch = ascending id
+        want = []
+        for t in p.tiles:
+            sx0, sy0, sx1, sy1 = p.support(t)
+            X0, Y0, X1, Y1 = t.x1 + sx0, t.y1 + sy0, t.x1 + sx1, t.y1 + sy1
+            if X1 > X0 and Y1 > Y0 and X0 < bx + bw and X1 > bx and Y0 < by + bh and Y1 > by:
+                want.append(t.idx)
+                cx0, cx1 = max(bx, X0) - t.x1, min(bx + bw, X1) - t.x1    # outputs of the back-resize this block needs
+                lo, hi = span(t.pw, t.ew, cx0, cx1 - cx0)
+                assert hi - lo <= wl.patch_w, ("blend", t.idx, hi - lo, wl.patch_w)
+                cy0, cy1 = max(by, Y0) - t.y1, min(by + bh, Y1) - t.y1
+                lo, hi = span(t.ph, t.eh, cy0, cy1 - cy0)
+                assert hi - lo <= wl.patch_h
+        assert listed == want, (bx, by)
+        for j in range(first, first + count):
+            assert (int(cover[j, 1]) & 0xFFFFFFFF) | (int(cover[j, 2]) << 32) == boffs[int(cover[j, 0])]
