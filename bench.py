@@ -86,6 +86,29 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def expected_digest(workload: str, world: int):
+    """SHA-256 of the u8 result the reference produces for this workload (tests/golden/bench_digests.json, written by
+    oracle/gen_bench_digests.py: the REAL reference's process_single_gpu for N = 1 where it was run, the oracle
+    otherwise; oracle.replay_static of the recorded assignment for N > 1).  -> (entry, key) or (None, key)."""
+    p = os.path.join(ROOT, "tests", "golden", "bench_digests.json")
+    key = f"{workload}/n{world}"
+    if not os.path.isfile(p):
+        return None, key
+    db = json.load(open(p))["digests"]
+    for src in ("reference", "oracle"):
+        if f"{key}/{src}" in db:
+            return db[f"{key}/{src}"], f"{key}/{src}"
+    return None, key
+
+
+def result_digest(out) -> str:
+    """SHA-256 of a result tensor [B,H,W,3] fp32 (values k/255, any device) as u8."""
+    import hashlib
+    import torch
+    q = torch.round(out.detach().to(torch.float32) * 255).to(torch.uint8).cpu().contiguous()
+    return hashlib.sha256(q.numpy().tobytes()).hexdigest()
+
+
 # --------------------------------------------------------------------------------------
 # CPU baseline (oracle/ref_port.py: the reference's Pillow path, same cost structure)
 # --------------------------------------------------------------------------------------
@@ -236,6 +259,35 @@ def main():
             td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    # ---- parity first: one untimed step per arm; rank 0's result against the committed digest of the reference --------
+    parity = {"checked": False, "match": None, "why": "no digest for this workload / sampler"}
+    exp, exp_key = expected_digest(args.workload, world)
+    if args.denoiser == "t0" and exp is not None:
+        out_dev, out_e2e = step_device(), step_e2e()
+        barrier()
+        ok = 1
+        if rank == 0:
+            got = {"device_arm": result_digest(out_dev), "e2e_arm": result_digest(out_e2e)}
+            plan0 = planner_mod.get_plan(W, H, tile, tile, pad, blur, True)
+            same_asg = world == 1 or [list(map(int, a)) for a in plan0.partition(world)] == exp.get("assignment")
+            match = same_asg and all(v == exp["sha256"] for v in got.values())
+            parity = {"checked": True, "match": bool(match), "source": f"tests/golden/bench_digests.json:{exp_key} ({exp['how']})",
+                      "expected": exp["sha256"], **got}
+            if not same_asg:
+                parity["why"] = "planner.partition differs from the assignment the digest was generated for"
+            ok = int(match)
+        del out_dev, out_e2e
+        flag = torch.tensor([ok], device=dev)
+        if world > 1:
+            td.broadcast(flag, 0)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "parity mismatch: the result differs from the reference's digest; nothing timed",
+                                  "parity": parity}))
+            if world > 1:
+                td.destroy_process_group()
+            sys.exit(3)
+
     for _ in range(max(args.warmup, 3)):
         step_device()
     clocks = ClockSampler(local)
@@ -371,6 +423,7 @@ def main():
                              "copies are serial around the distributed job")},
             "gpu_launches": stats.get("gpu_launches", 0) * args.steps,
             "gpu_launches_per_step": stats.get("gpu_launches", 0),
+            "parity": parity,
             "roofline": roofline}
     if t1_info is not None:
         line["sdxl_cost_tier"] = t1_info

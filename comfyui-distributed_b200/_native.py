@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 5
+ABI_VERSION = 6
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -64,6 +64,8 @@ _SIGNATURES = {
     "usdu_box_blur_params": (c_int, [c_float, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_quantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    "usdu_dequantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "usdu_pack_tiles_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "usdu_unpack_tiles_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "usdu_t0_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p]),
@@ -175,6 +177,14 @@ def box_blur_params(radius: float):
 # ---- device entry points (raw pointers; torch supplies memory and the stream) ----------
 def quantize_canvas(img_ptr, canvas_ptr, B, H, W, pitch, stream):
     _check(lib().usdu_quantize_canvas(img_ptr, canvas_ptr, B, H, W, pitch, stream), "usdu_quantize_canvas")
+
+
+def quantize_rows(img_ptr, canvas_ptr, B, H, W, pitch, y0, y1, stream):
+    _check(lib().usdu_quantize_rows(img_ptr, canvas_ptr, B, H, W, pitch, y0, y1, stream), "usdu_quantize_rows")
+
+
+def dequantize_rows(canvas_ptr, img_ptr, B, H, W, pitch, y0, y1, stream):
+    _check(lib().usdu_dequantize_rows(canvas_ptr, img_ptr, B, H, W, pitch, y0, y1, stream), "usdu_dequantize_rows")
 
 
 def dequantize_canvas(canvas_ptr, img_ptr, B, H, W, pitch, stream):

@@ -17,13 +17,16 @@ namespace usdu {
 // One thread produces 16 canvas bytes (one uint4 store) from 16 floats (4 x float4 loads).
 __global__ void __launch_bounds__(kThreads)
 quantize_canvas_kernel(const float* __restrict__ img, uint8_t* __restrict__ canvas, int rows, int W3,
-                       int64_t pitch, int vec_ok) {
+                       int64_t pitch, int vec_ok, int H, int y0, int n_rows) {
+    // logical row i of `rows` = B * n_rows  ->  physical row b * H + y0 + (i % n_rows)
     const int chunks = (W3 + 15) >> 4;
     const int64_t total = (int64_t)rows * chunks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / chunks;
-        const int j0 = (int)(i - row * chunks) << 4;
+        const int64_t lrow = i / chunks;
+        const int j0 = (int)(i - lrow * chunks) << 4;
+        const int64_t fb = lrow / n_rows;
+        const int64_t row = fb * H + y0 + (lrow - fb * n_rows);
         const float* src = img + row * W3 + j0;
         uint8_t* dst = canvas + row * pitch + j0;
         if (vec_ok && j0 + 16 <= W3) {
@@ -47,10 +50,12 @@ quantize_canvas_kernel(const float* __restrict__ img, uint8_t* __restrict__ canv
 // sector written whole by one instruction).  Rows on blockIdx.y, no integer division.
 __global__ void __launch_bounds__(kThreads)
 dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__ img, int rows, int W3,
-                         int64_t pitch, int vec_ok) {
+                         int64_t pitch, int vec_ok, int H, int y0, int n_rows) {
     if (vec_ok) {
         const int words = W3 >> 2;
-        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        for (int lrow = blockIdx.y; lrow < rows; lrow += gridDim.y) {
+            const int fb = lrow / n_rows;
+            const int64_t row = (int64_t)fb * H + y0 + (lrow - fb * n_rows);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(canvas + (int64_t)row * pitch);
             float4* dst = reinterpret_cast<float4*>(img + (int64_t)row * W3);
 #pragma unroll 4
@@ -66,9 +71,11 @@ dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__
         }
         return;
     }
-    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
-        const uint8_t* src = canvas + (int64_t)row * pitch;
-        float* dst = img + (int64_t)row * W3;
+    for (int lrow = blockIdx.y; lrow < rows; lrow += gridDim.y) {
+        const int fb = lrow / n_rows;
+        const int64_t row = (int64_t)fb * H + y0 + (lrow - fb * n_rows);
+        const uint8_t* src = canvas + row * pitch;
+        float* dst = img + row * W3;
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W3; j += gridDim.x * blockDim.x) dst[j] = dequant_u8_fast(src[j]);
     }
 }
@@ -445,37 +452,53 @@ using namespace usdu;
 
 extern "C" {
 
-int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
-                         void* stream) {
-    USDU_REQUIRE(img_dev && canvas_dev, "usdu_quantize_canvas: null pointer");
-    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_quantize_canvas: bad shape %dx%dx%d", B, H, W);
-    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_quantize_canvas: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
+int usdu_quantize_rows(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, int y0, int y1,
+                       void* stream) {
+    USDU_REQUIRE(img_dev && canvas_dev, "usdu_quantize_rows: null pointer");
+    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_quantize_rows: bad shape %dx%dx%d", B, H, W);
+    USDU_REQUIRE(0 <= y0 && y0 <= y1 && y1 <= H, "usdu_quantize_rows: bad row range [%d, %d) of %d", y0, y1, H);
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_quantize_rows: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
+    if (y1 == y0) return USDU_OK;
     const int W3 = W * 3;
     const int vec_ok = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0) && (((uintptr_t)canvas_dev & 15) == 0);
-    const int64_t total = (int64_t)B * H * ((W3 + 15) / 16);
+    const int64_t total = (int64_t)B * (y1 - y0) * ((W3 + 15) / 16);
     const int grid = grid_for((total + kThreads - 1) / kThreads);
-    quantize_canvas_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img_dev, canvas_dev, B * H, W3, pitch, vec_ok);
+    quantize_canvas_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img_dev, canvas_dev, B * (y1 - y0), W3, pitch, vec_ok, H, y0, y1 - y0);
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
+                         void* stream) {
+    USDU_REQUIRE(H > 0, "usdu_quantize_canvas: bad shape %dx%dx%d", B, H, W);
+    return usdu_quantize_rows(img_dev, canvas_dev, B, H, W, pitch, 0, H, stream);
+}
+
+int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W, int64_t pitch, int y0, int y1,
+                         void* stream) {
+    USDU_REQUIRE(img_dev && canvas_dev, "usdu_dequantize_rows: null pointer");
+    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_dequantize_rows: bad shape %dx%dx%d", B, H, W);
+    USDU_REQUIRE(0 <= y0 && y0 <= y1 && y1 <= H, "usdu_dequantize_rows: bad row range [%d, %d) of %d", y0, y1, H);
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_dequantize_rows: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
+    if (y1 == y0) return USDU_OK;
+    const int W3 = W * 3;
+    const int vec_ok = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0) && (((uintptr_t)canvas_dev & 15) == 0);
+    const int per_row = vec_ok ? W3 / 4 : W3;
+    int gx = (per_row + kThreads * 4 - 1) / (kThreads * 4);          // ~4 items per thread along a row
+    if (gx < 1) gx = 1;
+    int64_t gy = (int64_t)B * (y1 - y0);
+    if (gy > 65535) gy = 65535;
+    if (gy * gx > 148 * 16) gy = (148 * 16 + gx - 1) / gx;
+    if (gy < 1) gy = 1;
+    dequantize_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * (y1 - y0), W3, pitch, vec_ok, H, y0, y1 - y0);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
 
 int usdu_dequantize_canvas(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W, int64_t pitch,
                            void* stream) {
-    USDU_REQUIRE(img_dev && canvas_dev, "usdu_dequantize_canvas: null pointer");
-    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_dequantize_canvas: bad shape %dx%dx%d", B, H, W);
-    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_dequantize_canvas: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
-    const int W3 = W * 3;
-    const int vec_ok = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0) && (((uintptr_t)canvas_dev & 15) == 0);
-    const int per_row = vec_ok ? W3 / 4 : W3;
-    int gx = (per_row + kThreads * 4 - 1) / (kThreads * 4);          // ~4 items per thread along a row
-    if (gx < 1) gx = 1;
-    int64_t gy = (int64_t)B * H;
-    if (gy > 65535) gy = 65535;
-    if (gy * gx > 148 * 16) gy = (148 * 16 + gx - 1) / gx;
-    if (gy < 1) gy = 1;
-    dequantize_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * H, W3, pitch, vec_ok);
-    USDU_CUDA(cudaGetLastError());
-    return USDU_OK;
+    USDU_REQUIRE(H > 0, "usdu_dequantize_canvas: bad shape %dx%dx%d", B, H, W);
+    return usdu_dequantize_rows(canvas_dev, img_dev, B, H, W, pitch, 0, H, stream);
 }
 
 int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* stream) {

@@ -7,6 +7,7 @@ upscale/modes/static.py (per-participant canvases, sorted final blend :521-553).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -110,18 +111,18 @@ class DevicePlan:
         cover = torch.from_numpy(wl.cover).to(self.device) if wl.cover is not None else None
         return items, cover
 
-    def crop_list(self, tile_ids: Tuple[int, ...], B: int, use_fast: bool):
-        key = ("crop", tile_ids, B, use_fast)
+    def crop_list(self, tile_ids: Tuple[int, ...], B: int, use_fast: bool, share: int = 1):
+        key = ("crop", tile_ids, B, use_fast, share)
         if key not in self._wl:
-            wl, offs, total = self.plan.crop_worklist(tile_ids, B, use_fast)
+            wl, offs, total = self.plan.crop_worklist(tile_ids, B, use_fast, share)
             self._wl[key] = (wl, offs, total) + self._upload(wl)
         return self._wl[key]
 
     def blend_list(self, tile_ids: Tuple[int, ...], offs: np.ndarray, src_u8: bool, use_fast: bool, B: int = 1,
-                   part: Optional[Tuple[int, int]] = None):
-        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast, B, part)
+                   part: Optional[Tuple[int, int]] = None, share: int = 1):
+        key = ("blend", tile_ids, tuple(int(o) for o in offs), src_u8, use_fast, B, part, share)
         if key not in self._wl:
-            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast, B, part)
+            wl = self.plan.blend_worklist(tile_ids, offs, 1 if src_u8 else 4, use_fast, B, part, share)
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
@@ -142,6 +143,7 @@ class Canvas:
         self.launches = 0
         self.algo_bytes = 0
         self.flags = nat.FLAG_FAST if (self.plan.fast and not FORCE_GENERIC) else 0
+        self.share = 1                      # launches expected to run side by side (tile-granular schedule)
 
     @staticmethod
     def pitch_of(W: int) -> int:
@@ -182,7 +184,7 @@ class Canvas:
         """-> (flat fp32 buffer, element offsets per tile).  Tile i is
         buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
         tile_ids = tuple(int(t) for t in tile_ids)
-        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, bool(self.flags & nat.FLAG_FAST))
+        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, bool(self.flags & nat.FLAG_FAST), self.share)
         if out is None:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
@@ -209,7 +211,8 @@ class Canvas:
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B, part)
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B, part,
+                                              1 if part is not None else self.share)
         if items.shape[0] == 0:
             return
         p = self.plan
@@ -324,6 +327,63 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     return shipped
 
 
+SCHEDULE = os.environ.get("USDU_SCHEDULE", "waves")     # waves | dag
+
+
+def use_dag(plan: Plan, order: Sequence[int]) -> bool:
+    """Level waves by default.  The tile-granular schedule (USDU_SCHEDULE=dag) shortens the critical path from 31
+    waves to 31 single-tile chains, but on B200 with a T0-cost sampler it is SLOWER (cfg2: 1.546 vs 1.346 ms,
+    profiles/r02a_*): 405 graph kernel nodes on 9 streams are bound by the ~3.4 us/node launch rate of the graph,
+    not by the chain.  It pays only when the sampler call is long enough to hide node launches but too small to
+    fill the machine with one tile."""
+    return SCHEDULE == "dag" and len(plan.waves(order)) > 2
+
+
+def run_dag(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, lanes: List["torch.cuda.Stream"],
+            payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()):
+    """The same job as run_progressive(order) as a tile-granular DAG (planner.Plan.dag): one crop -> sampler ->
+    blend chain per tile, chains on `lanes` (CUDA streams) joined by events only where covers intersect.  Meant to
+    be stream-captured (GraphedWaves): level k+1's crops then overlap level k's blends of unrelated tiles, and the
+    critical path is 31 single-tile chains instead of 31 whole waves (single_gpu.py:40-64 fixes only the ORDER of
+    overlapping tiles).  The caller's current stream forks into the lanes and joins them at the end."""
+    plan, B = canvas.plan, canvas.B
+    order = [int(t) for t in order]
+    lane_of, waits = plan.dag(order)
+    main = torch.cuda.current_stream(canvas.buf.device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    used = sorted(set(lane_of))
+    for ln in used:
+        lanes[ln].wait_event(fork)
+    waited = {w for ws in waits for w in ws}
+    done: Dict[int, torch.cuda.Event] = {}
+    canvas.share = max(1, min(len(used), 16))
+    try:
+        for i, tid in enumerate(order):
+            st = lanes[lane_of[i]]
+            for w in waits[i]:
+                st.wait_event(done[w])
+            with torch.cuda.stream(st):
+                if "crop" in skip:
+                    offs, total = plan.slot_offsets([tid], B)
+                    buf = torch.empty(total, dtype=torch.float32, device=canvas.buf.device)   # timing variant: contents unused
+                else:
+                    buf, offs = canvas.crop([tid])
+                out = denoise_packed(plan, [tid], buf, offs, B, denoiser)
+                if "blend" not in skip:
+                    canvas.blend([tid], out, offs)
+                if payload is not None:
+                    nat.pack_tiles_u8(out.data_ptr(), payload[where[tid][1]:].data_ptr(), out.numel(), _stream_ptr())
+                    canvas.launches += 1
+                if i in waited:
+                    done[i] = torch.cuda.Event()
+                    done[i].record(st)
+    finally:
+        canvas.share = 1
+    for ln in used:
+        main.wait_stream(lanes[ln])
+
+
 class GraphedWaves:
     """The wave loop of a progressive job (crop -> sampler -> blend, x waves) captured once
     into a CUDA graph on a static canvas: one graph launch replaces ~5 kernel launches per
@@ -347,8 +407,18 @@ class GraphedWaves:
         side.wait_stream(torch.cuda.current_stream(dp.device))
         saved = PROFILE
         PROFILE = None
+        # tile-granular DAG on several streams (no per-kernel profile, no tile dictionary: those stay wave mode)
+        self.dag = bool(order) and profile is None and not keep_processed and use_dag(dp.plan, order)
+        lanes = [torch.cuda.Stream(device=dp.device) for _ in range(max(dp.plan.dag(order)[0]) + 1)] if self.dag else []
+
+        def body():
+            if self.dag:
+                run_dag(self.canvas, order, denoiser, lanes, self.payload, where, skip)
+                return {}
+            return run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
+
         with torch.cuda.stream(side):                 # warm-up: fills every cache (work lists, noise)
-            run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
+            body()
         torch.cuda.current_stream(dp.device).wait_stream(side)
         torch.cuda.synchronize(dp.device)
         self.canvas.launches = 0
@@ -359,7 +429,7 @@ class GraphedWaves:
             profile.capturing = True
         try:
             with torch.cuda.graph(self.graph):
-                self.shipped = run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
+                self.shipped = body()
         finally:
             PROFILE = saved
             if profile is not None:
@@ -374,7 +444,7 @@ class GraphedWaves:
             canvas_buf: Optional[torch.Tensor] = None) -> "GraphedWaves":
         pkey = None if payload is None else (payload.data_ptr(), payload.numel())
         ckey = None if canvas_buf is None else canvas_buf.data_ptr()
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC,
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, SCHEDULE,
                None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:

@@ -305,6 +305,59 @@ class Plan:
             out[lv].append(t)
         return out
 
+    # ---- tile-granular dependency graph ------------------------------------------------
+    def cover(self, t: Tile) -> Tuple[int, int, int, int]:
+        """Canvas rectangle a blend launch of tile t may LOAD AND STORE: its crop window grown to the block grid
+        of the kernels (128-px columns; rows for any block height up to FAST_BLOCK_H).  The blend kernels move
+        whole canvas blocks, so two tiles may run concurrently only if their covers are disjoint, not merely
+        their windows (a block shared by two concurrent launches would lose one of the two updates)."""
+        bw, bh = nat.FAST_BLOCK_W, nat.FAST_BLOCK_H
+        return (t.x1 // bw * bw, t.y1 - (bh - 1), (t.x2 + bw - 1) // bw * bw, t.y2 + (bh - 1))
+
+    MAX_LANES = 48
+
+    def dag(self, order: Optional[Sequence[int]] = None) -> Tuple[List[int], List[List[int]]]:
+        """The progressive job as a tile-granular DAG instead of level waves: tile k's chain (crop -> sampler ->
+        blend) may start as soon as the chains of the earlier tiles whose covers intersect its own are done --
+        which is all upscale/modes/single_gpu.py:40-64 requires, any topological order gives the same canvas.
+        -> (lane[i], waits[i]) for the i-th tile of `order`: the tile runs on stream `lane[i]` after the tiles at
+        positions `waits[i]` of other lanes (same-lane predecessors are ordered by the stream).  Lanes follow the
+        grid rows of a full canvas (tile (r, c) continues the lane of (r, c-1) and waits for (r-1, c+1)); tiles
+        without dependencies (a conflict-free partition) spread over up to MAX_LANES lanes."""
+        order = list(range(len(self.tiles))) if order is None else [int(t) for t in order]
+        pos = {t: i for i, t in enumerate(order)}
+        covers = {t: self.cover(self.tiles[t]) for t in order}
+        cell_w = max(c[2] - c[0] for c in covers.values()) if covers else 1
+        cell_h = max(c[3] - c[1] for c in covers.values()) if covers else 1
+        buckets: Dict[Tuple[int, int], List[int]] = {}
+        lane_of: List[int] = []
+        waits: List[List[int]] = []
+        tails: List[int] = []                       # position of the last tile queued on each lane
+        for i, t in enumerate(order):
+            c = covers[t]
+            cells = [(gx, gy) for gx in range(c[0] // cell_w, (c[2] - 1) // cell_w + 1)
+                     for gy in range(c[1] // cell_h, (c[3] - 1) // cell_h + 1)]
+            deps = sorted({pos[o] for cell in cells for o in buckets.get(cell, ()) if _overlap(covers[o], c)})
+            for cell in cells:
+                buckets.setdefault(cell, []).append(t)
+            dset = set(deps)
+            cand = [ln for ln, tail in enumerate(tails) if tail in dset]
+            if cand:
+                ln = max(cand, key=lambda q: tails[q])
+            elif len(tails) < self.MAX_LANES:
+                ln = len(tails)
+                tails.append(-1)
+            else:
+                ln = min(range(len(tails)), key=lambda q: tails[q])
+            latest: Dict[int, int] = {}
+            for d in deps:
+                if lane_of[d] != ln:
+                    latest[lane_of[d]] = max(latest.get(lane_of[d], -1), d)
+            lane_of.append(ln)
+            waits.append(sorted(latest.values()))
+            tails[ln] = i
+        return lane_of, waits
+
     def conflict_free(self, assignment: Sequence[Sequence[int]]) -> bool:
         for tiles in assignment:
             s = set(tiles)
@@ -359,12 +412,14 @@ class Plan:
 
     SLOTS = 148 * 4            # resident CTAs of the fast kernels on a B200 (4 per SM)
 
-    def block_shape(self, use_fast: bool, extents: Optional[Sequence[Tuple[int, int]]] = None, frames: int = 1) -> Tuple[int, int]:
+    def block_shape(self, use_fast: bool, extents: Optional[Sequence[Tuple[int, int]]] = None, frames: int = 1,
+                    share: int = 1) -> Tuple[int, int]:
         """Block edge of a launch.  `extents` = (width, height) in pixels each tile covers in
         the launch's block space.  The block height is chosen by a simple wave model:
         cost(bh) = ceil(#CTAs / resident slots) * (bh + halo/fixed rows) -- short blocks give
         small (latency bound) launches more CTAs, and large launches avoid a nearly empty
-        last wave."""
+        last wave.  share = launches expected to run side by side (tile-granular schedule): each gets
+        1/share of the machine."""
         if not use_fast:
             return self._generic_block
         bw = nat.FAST_BLOCK_W
@@ -373,7 +428,7 @@ class Plan:
         best = None
         for bh in (8, 12, 16, 20, 24, 28, 32):
             n = sum(((w + bw - 1) // bw + 1) * ((h + bh - 1) // bh + 1) for w, h in extents) * frames   # +1: unaligned windows
-            cost = math.ceil(n / self.SLOTS) * (bh + 12)
+            cost = math.ceil(n / max(self.SLOTS // max(share, 1), 1)) * (bh + 12)
             if best is None or cost < best[0] or (cost == best[0] and bh > best[1]):
                 best = (cost, bh)
         return bw, best[1]
@@ -406,13 +461,14 @@ class Plan:
                 return bh
         return 8
 
-    def crop_worklist(self, tile_ids: Sequence[int], B: int, use_fast: Optional[bool] = None) -> Tuple[WorkList, np.ndarray, int]:
+    def crop_worklist(self, tile_ids: Sequence[int], B: int, use_fast: Optional[bool] = None,
+                      share: int = 1) -> Tuple[WorkList, np.ndarray, int]:
         use_fast = self.fast if use_fast is None else (use_fast and self.fast)
         offs, total = self.slot_offsets(tile_ids, B)
         rows = []
         pw_max = ph_max = 1
         nbytes = 0
-        bw, bh_max = self.block_shape(use_fast, [(self.tiles[t].pw - nat.FAST_BLOCK_W, self.tiles[t].ph) for t in tile_ids], B)
+        bw, bh_max = self.block_shape(use_fast, [(self.tiles[t].pw - nat.FAST_BLOCK_W, self.tiles[t].ph) for t in tile_ids], B, share)
         for i, tid in enumerate(tile_ids):
             t = self.tiles[tid]
             bh = self._crop_block_rows(t, use_fast, bh_max)
@@ -476,7 +532,8 @@ class Plan:
         return J
 
     def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
-                       use_fast: Optional[bool] = None, B: int = 1, part: Optional[Tuple[int, int]] = None) -> WorkList:
+                       use_fast: Optional[bool] = None, B: int = 1, part: Optional[Tuple[int, int]] = None,
+                       share: int = 1) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
         given order (the order of `tile_ids` IS the blend order).  part = (i, n): only the i-th of n
         equal shares of the (sorted) block list -- every block is owned by exactly one CTA, so n
@@ -486,7 +543,7 @@ class Plan:
         for t in tile_ids:
             sx0, sy0, sx1, sy1 = self.support(self.tiles[t])
             ext.append((sx1 - sx0, sy1 - sy0))
-        bw, bh = self.block_shape(use_fast, ext, B)
+        bw, bh = self.block_shape(use_fast, ext, B, share)
         nbx = (self.W + bw - 1) // bw
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 5
+#define USDU_ABI_VERSION 6
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -205,6 +205,14 @@ int usdu_quantize_canvas(const float* img_dev, uint8_t* canvas_dev, int B, int H
 /* canvas u8 -> fp32 image (u / 255.0f, utils/image.py:12-14) */
 int usdu_dequantize_canvas(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W,
                            int64_t pitch, void* stream);
+/* The same two casts on canvas rows [y0, y1) of EVERY frame (img_dev / canvas_dev are the bases of the whole
+ * [B][H][W][3] image and [B][H][pitch] canvas).  Multi-GPU jobs quantise, composite and dequantise the canvas slab by
+ * slab: canvas_dev of usdu_dequantize_rows may be a PEER's canvas mapped over NVLink (the master gathers the final
+ * slabs of all ranks while it dequantises, upscale/modes/static.py:556-564 'result tensor'). */
+int usdu_quantize_rows(const float* img_dev, uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
+                       int y0, int y1, void* stream);
+int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W, int64_t pitch,
+                         int y0, int y1, void* stream);
 /* Q1 for transport: dst[i] = (uint8)(255.f * src[i]); n elements (worker_comms.py:30-33) */
 int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* stream);
 /* receiving side of the transport: dst[i] = src[i] / 255.0f (api/job_routes.py:104-132) */
