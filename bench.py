@@ -337,6 +337,21 @@ def main():
         kern = prof.summary()
         timing_note = "CUDA events around every launch of one step after the timed region"
 
+    # ---- N > 1: where the step goes, per phase, max over ranks (CUDA events at the phase boundaries) -----------------
+    phases = None
+    if world > 1:
+        acc = {}
+        for _ in range(5):
+            st = {"time_phases": True}
+            step_device(st)
+            for k_, v_ in st.get("phase_ms", {}).items():
+                acc.setdefault(k_, []).append(v_)
+        if acc:
+            names = list(acc)
+            t = torch.tensor([sorted(acc[n_])[len(acc[n_]) // 2] for n_ in names], device=dev)     # median of 5 per rank
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            phases = {n_: round(float(v_), 4) for n_, v_ in zip(names, t.tolist())}
+
     # ---- end to end through the node API (host tensor in, host tensor out) -------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(max(args.warmup, 3)):
@@ -419,12 +434,15 @@ def main():
                     "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
                     "api": "UltimateSDUpscaleDistributed.run(host tensor) -> host tensor",
                     "note": ("upload, kernels and download overlap band by band (engine.HostPipeline)" if world == 1 else
-                             "every rank uploads the replicated canvas (like the reference's workers), rank 0 downloads the result; "
-                             "copies are serial around the distributed job")},
+                             "every rank uploads and downloads only its slab (1/N of the rows) over its own PCIe link; the quantised "
+                             "slabs are exchanged over NVLink; the result lands in one page-locked shared-memory tensor "
+                             "(dist.upscale_static_host); h2d/d2h bytes are the job's totals over all ranks")},
             "gpu_launches": stats.get("gpu_launches", 0) * args.steps,
             "gpu_launches_per_step": stats.get("gpu_launches", 0),
             "parity": parity,
             "roofline": roofline}
+    if phases is not None:
+        line["phase_ms_max_over_ranks"] = phases
     if t1_info is not None:
         line["sdxl_cost_tier"] = t1_info
     if not args.no_cpu_baseline and world == 1:

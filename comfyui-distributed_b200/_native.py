@@ -25,6 +25,7 @@ T_FULL_X0, T_FULL_Y0, T_FULL_X1, T_FULL_Y1 = 16, 17, 18, 19
 TAB_HEADER = 8
 PACKED_ROW = 8
 FLAG_FAST = 1
+FLAG_MMA = 2
 FLAG_REMOTE_CANVAS = 1 << 24
 FILTER_LANCZOS, FILTER_BICUBIC = 0, 1
 CROP_ITEM_WORDS = 6

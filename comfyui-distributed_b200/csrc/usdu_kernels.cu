@@ -448,6 +448,14 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
                  int patch_h, const void* src, int src_is_u8, int block_rows, int remote, cudaStream_t st);
 } }
 
+namespace usdu { namespace mma {
+int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
+                int patch_w, int patch_h, float* out, cudaStream_t st);
+int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
+                 const int32_t* items, int n_items, int patch_w, int patch_h, const void* src, int src_is_u8, int block_rows,
+                 cudaStream_t st);
+} }
+
 using namespace usdu;
 
 extern "C" {
@@ -617,6 +625,10 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
     USDU_REQUIRE(patch_w > 0 && patch_h > 0, "usdu_tile_crop_resize: patch capacity must be positive");
     if (n_items == 0) return USDU_OK;
     USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_crop_resize: pitch must be >= 3*W and a multiple of 16");
+    if (flags & USDU_FLAG_MMA) {
+        USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: tensor-core path needs tables");
+        return mma::launch_crop(canvas_dev, B, H, W, pitch, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev, (cudaStream_t)stream);
+    }
     if (flags & USDU_FLAG_FAST) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: fast path needs tables");
         return fast::launch_crop(canvas_dev, B, H, W, pitch, tiles_dev, tabs_dev, items_dev, n_items, patch_w, patch_h,
@@ -639,13 +651,19 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, con
                     const int32_t* tabs_dev, const uint8_t* mask_pool_dev, const int32_t* items_dev,
                     int n_items, const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
                     int src_is_u8, int flags, void* stream) {
-    USDU_REQUIRE(canvas_dev && tiles_dev && mask_pool_dev && items_dev && src_dev && (cover_dev || (flags & USDU_FLAG_FAST)),
+    USDU_REQUIRE(canvas_dev && tiles_dev && mask_pool_dev && items_dev && src_dev && (cover_dev || (flags & (USDU_FLAG_FAST | USDU_FLAG_MMA))),
                  "usdu_tile_blend: null pointer");
     USDU_REQUIRE(B > 0 && H > 0 && W > 0 && n_items >= 0, "usdu_tile_blend: bad shape");
     USDU_REQUIRE(B <= 65535, "usdu_tile_blend: batch %d exceeds grid.y limit", B);
     USDU_REQUIRE(patch_w > 0 && patch_h > 0, "usdu_tile_blend: patch capacity must be positive");
     if (n_items == 0) return USDU_OK;
     USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_blend: pitch must be >= 3*W and a multiple of 16");
+    if (flags & USDU_FLAG_MMA) {
+        USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: tensor-core path needs tables");
+        USDU_REQUIRE(((uintptr_t)src_dev & 15) == 0, "usdu_tile_blend: src must be 16-byte aligned");
+        return mma::launch_blend(canvas_dev, B, H, W, pitch, tabs_dev, mask_pool_dev, items_dev, n_items, patch_w, patch_h, src_dev,
+                                 src_is_u8, (flags >> 8) & 0xFF, (cudaStream_t)stream);
+    }
     if (flags & USDU_FLAG_FAST) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: fast path needs tables");
         USDU_REQUIRE(((uintptr_t)src_dev & 15) == 0, "usdu_tile_blend: src must be 16-byte aligned");

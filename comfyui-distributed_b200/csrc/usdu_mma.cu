@@ -1,0 +1,564 @@
+// usdu_mma.cu -- tensor-core crop+LANCZOS and LANCZOS-back+composite kernels (sm_100a).
+//
+// Pillow's 8-bit resampling pass is a banded integer contraction, out[o] = clip8((2^21 + sum_k in[k] * coef[o][k]) >> 22)
+// with 23-bit signed coefficients.  On the CUDA-core integer pipes a tap costs one PRMT + one IMAD per byte
+// (usdu_fast.cuh: 5.0 output bytes/clk/SM, the kernels were ALU-pipe bound at 0.20 of the HBM roofline).  Here the taps
+// run on the tensor cores: mma.sync.m16n8k32 multiplies u8 pixels by 8-bit LIMBS of the coefficients
+// (coef = l2 * 65536 + l1 * 256 + l0; l0, l1 unsigned, l2 signed) with exact s32 accumulation, three IMMAs per
+// 16 x 8 x 32 tile, recombined with two shift-adds.  |limb sum| <= 64 * 255 * 255 < 2^23, and the recombined value is
+// Pillow's accumulator exactly, so the results stay bit-identical (tools/ubench/imma.cu: probe + 7.7 / 9.5 B/clk/SM).
+//
+// Both passes put the COEFFICIENTS in the A operand (16 outputs x 32 inputs, built on the host in fragment order:
+// planner.build_mma_frags) and the PIXELS in B:
+//   H pass  M = 16 output pixels of one channel, N = 8 rows, K = 32 input pixels.  Input staged PLANAR (one byte
+//           plane per channel), so a B register is 4 consecutive pixels of a row: one aligned LDS.32.
+//   V pass  M = 16 output rows, N = 8 byte columns, K = 32 input rows.  The H pass leaves its u8 results ROW-PACKED,
+//           word(kg, col) = rows 4kg..4kg+3 of byte column col, so a B register is again one LDS.32.
+// A thread owns 2 x 2 results of a 16 x 8 tile; two N-tiles are run side by side and neighbouring lanes swap halves
+// (one SHFL) so that every thread ends with 4 consecutive rows (H) or 4 consecutive bytes (V) to pack into one word.
+// Shared-memory pitches (plane rows == 16 mod 32 bytes, row groups == 24 mod 32 words) keep every fragment load and
+// every store on 32 distinct banks.
+#include "usdu_common.cuh"
+#include "usdu_tma.cuh"
+#include <string.h>
+
+namespace usdu {
+namespace mma {
+
+constexpr int kT = 256;                     // 8 warps
+constexpr int BWX = USDU_FAST_BLOCK_W;      // 128-pixel wide blocks
+constexpr int MIDP = 440;                   // words per row group of the intermediate: >= 3 * 144 columns, == 24 mod 32
+constexpr int kDBox = BWX * 3 / 2;          // canvas block = two bulk-tensor boxes of 192 bytes per row
+constexpr int kBoxB = 256, kBoxR = 48;      // crop: raw canvas patch = two boxes of 256 bytes x 48 rows
+
+__host__ __device__ inline int plane_pitch(int patch_w) { return (patch_w + 31) / 32 * 32 + 16; }   // bytes, == 16 mod 32
+__host__ __device__ inline size_t planes_bytes(int patch_w, int plane_rows) { return (size_t)3 * plane_rows * plane_pitch(patch_w); }
+__host__ __device__ inline size_t mid_bytes(int mid_rows) { return (size_t)(mid_rows / 4) * MIDP * 4; }
+constexpr size_t kHeadBytes = USDU_JOB_WORDS * 4;
+
+struct JobView {
+    const int32_t* j;
+    __device__ __forceinline__ int operator[](int i) const { return j[i]; }
+    __device__ __forceinline__ int64_t i64(int lo) const { return (int64_t)(uint32_t)j[lo] | ((int64_t)j[lo + 1] << 32); }
+};
+
+__device__ __forceinline__ void load_job(int32_t* job_sm, const int32_t* __restrict__ jobs, int idx) {
+    if (threadIdx.x < USDU_JOB_WORDS / 4)
+        reinterpret_cast<int4*>(job_sm)[threadIdx.x] = __ldg(reinterpret_cast<const int4*>(jobs + (size_t)idx * USDU_JOB_WORDS) + threadIdx.x);
+}
+
+// D = A (16 x 32, coefficients) * B (32 x 8, u8 pixels) + C, s32
+__device__ __forceinline__ void mma_uu(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_su(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Pillow's clip8((acc) >> 22) of the recombined limbs (limb 0 starts at the rounding constant 2^21)
+__device__ __forceinline__ uint32_t finish(int l0, int l1, int l2) {
+    const int acc = l0 + (l1 << 8) + (l2 << 16);
+    return (uint32_t)__vimin_s32_relu(acc >> kPrecisionBits, 255);
+}
+
+// fragment section of a table (planner.build_mma_frags)
+struct FragTable {
+    const int32_t* base;       // tabs + section
+    int n_mt, fbase;
+    __device__ __forceinline__ FragTable(const int32_t* tabs, int section) : base(tabs + section) {
+        n_mt = __ldg(base);
+        fbase = 4 + ((n_mt + 3) & ~3);
+    }
+    __device__ __forceinline__ int k0(int mt) const { return __ldg(base + 4 + mt); }
+    template <int KS>
+    __device__ __forceinline__ void load(uint32_t (&a)[KS][3][4], int mt, int lane) const {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(base + fbase) + ((mt * KS + ks) * 3 + l) * 32 + lane);
+                a[ks][l][0] = q.x; a[ks][l][1] = q.y; a[ks][l][2] = q.z; a[ks][l][3] = q.w;
+            }
+    }
+};
+
+// Two N-tiles (A: n = 0..7, B: n = 8..15) of one M-tile -> per row half h (m = g, g + 8) one word of 4 consecutive
+// n.  Lane t holds n = 2t, 2t+1 of both tiles; lanes t and t^1 swap so that even t gets n = 4(t/2)..+3 (tile A) and
+// odd t gets n = 8 + 4(t/2)..+3 (tile B).  Returns the 4-group index within the 16 (0..3).
+__device__ __forceinline__ int pack16(const int (&dA)[3][4], const int (&dB)[3][4], int t, uint32_t (&word)[2]) {
+    uint32_t pA[2], pB[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        pA[h] = finish(dA[0][2 * h], dA[1][2 * h], dA[2][2 * h]) | (finish(dA[0][2 * h + 1], dA[1][2 * h + 1], dA[2][2 * h + 1]) << 8);
+        pB[h] = finish(dB[0][2 * h], dB[1][2 * h], dB[2][2 * h]) | (finish(dB[0][2 * h + 1], dB[1][2 * h + 1], dB[2][2 * h + 1]) << 8);
+    }
+    const bool odd = t & 1;
+    const uint32_t send = odd ? (pA[0] | (pA[1] << 16)) : (pB[0] | (pB[1] << 16));
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    if (!odd) {
+        word[0] = pA[0] | (recv << 16);
+        word[1] = pA[1] | (recv & 0xffff0000u);
+    } else {
+        word[0] = (recv & 0xffffu) | (pB[0] << 16);
+        word[1] = (recv >> 16) | (pB[1] << 16);
+    }
+    return (t >> 1) + (odd ? 2 : 0);
+}
+
+__device__ __forceinline__ void init_acc(int (&d)[3][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { d[0][i] = 1 << (kPrecisionBits - 1); d[1][i] = 0; d[2][i] = 0; }
+}
+
+// geometry of the block along the horizontal axis (shared by both passes: the V pass needs the column offset)
+struct HGeo {
+    int mt0, mt1, o_org, coff;
+    __device__ __forceinline__ HGeo(const JobView& J) {
+        const int oxb = J[USDU_J_OX_BASE];
+        mt0 = max(oxb, 0) >> 4;
+        mt1 = (min(oxb + BWX, J[USDU_J_N_OUT_H]) - 1) >> 4;
+        o_org = min(oxb, mt0 << 4);            // output index of column 0 of the intermediate
+        coff = 3 * (oxb - o_org);              // byte column of the intermediate that is block byte 0
+    }
+};
+
+// ---- H pass: planes -> mid (row-packed) ---------------------------------------------------------------------------
+template <int KS>
+__device__ __forceinline__ void hpass(const uint8_t* __restrict__ planes, uint32_t* __restrict__ mid, const int32_t* __restrict__ tabs,
+                                      const JobView& J, int PB, int plane_rows, int steps16) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const FragTable F(tabs, J[USDU_J_ROWS_H]);
+    const HGeo G(J);
+    const int sx0 = J[USDU_J_IX0];
+    for (int mt = G.mt0 + w; mt <= G.mt1; mt += kT / 32) {
+        uint32_t a[KS][3][4];
+        F.load<KS>(a, mt, lane);
+        const int krel = F.k0(mt) - sx0;                       // >= 0, multiple of 4
+        const int col0 = 3 * ((mt << 4) + g - G.o_org);
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+            const uint8_t* pl = planes + (size_t)c * plane_rows * PB + krel + 4 * t + g * PB;
+#pragma unroll 1
+            for (int s = 0; s < steps16; ++s) {
+                const uint8_t* pa = pl + (size_t)(16 * s) * PB;
+                int dA[3][4], dB[3][4];
+                init_acc(dA); init_acc(dB);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa + 32 * ks), a1 = *reinterpret_cast<const uint32_t*>(pa + 32 * ks + 16);
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pa + 8 * PB + 32 * ks), b1 = *reinterpret_cast<const uint32_t*>(pa + 8 * PB + 32 * ks + 16);
+                    mma_uu(dA[0], a[ks][0], a0, a1); mma_uu(dA[1], a[ks][1], a0, a1); mma_su(dA[2], a[ks][2], a0, a1);
+                    mma_uu(dB[0], a[ks][0], b0, b1); mma_uu(dB[1], a[ks][1], b0, b1); mma_su(dB[2], a[ks][2], b0, b1);
+                }
+                uint32_t word[2];
+                const int kg = 4 * s + pack16(dA, dB, t, word);  // 4 consecutive ROWS of outputs m = g (word 0) and g + 8 (word 1)
+                mid[kg * MIDP + col0 + c] = word[0];
+                mid[kg * MIDP + col0 + 24 + c] = word[1];
+            }
+        }
+    }
+}
+
+// ---- V pass: mid -> 4-byte strips of block rows, handed to an epilogue -----------------------------------------------
+// Epilogue::prefetch(r0, r1, strip) issues the loads the epilogue will need for block rows r0, r1 BEFORE the MMAs;
+// Epilogue::store(pre, h, r, strip, word) consumes them (bytes 4 strip .. 4 strip + 3 of block row r).
+template <int KS, class Epilogue>
+__device__ __forceinline__ void vpass(const uint32_t* __restrict__ mid, const int32_t* __restrict__ tabs, const JobView& J, int bh,
+                                      Epilogue& epi) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const FragTable F(tabs, J[USDU_J_ROWS_V]);
+    const HGeo G(J);
+    const int oyb = J[USDU_J_OY_BASE], sy0 = J[USDU_J_IY0];
+    const int mv0 = max(oyb, 0) >> 4, mv1 = (min(oyb + bh, J[USDU_J_N_OUT_V]) - 1) >> 4;
+    constexpr int PAIRS = BWX * 3 / 16;                        // 24 pairs of N-tiles = 384 byte columns
+    const int units = (mv1 - mv0 + 1) * PAIRS;
+    int cur = -1, kgbase = 0;
+    uint32_t a[KS][3][4];
+    const int sub = (t >> 1) + ((t & 1) ? 2 : 0);               // which 4-byte strip of the pair this lane ends with
+#pragma unroll 1
+    for (int u = w; u < units; u += kT / 32) {
+        const int mv = mv0 + u / PAIRS, p = u - (u / PAIRS) * PAIRS;
+        if (mv != cur) {
+            F.load<KS>(a, mv, lane);
+            kgbase = (F.k0(mv) - sy0) >> 2;
+            cur = mv;
+        }
+        const int r0 = (mv << 4) + g - oyb;                     // block row of output m = g; m = g + 8 is r0 + 8
+        const int strip = 4 * p + sub;
+        const typename Epilogue::Pre pre = epi.prefetch(r0, r0 + 8, strip);
+        const uint32_t* mp = mid + (kgbase + t) * MIDP + G.coff + 16 * p + g;
+        int dA[3][4], dB[3][4];
+        init_acc(dA); init_acc(dB);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t a0 = mp[(8 * ks) * MIDP], a1 = mp[(8 * ks + 4) * MIDP];
+            const uint32_t b0 = mp[(8 * ks) * MIDP + 8], b1 = mp[(8 * ks + 4) * MIDP + 8];
+            mma_uu(dA[0], a[ks][0], a0, a1); mma_uu(dA[1], a[ks][1], a0, a1); mma_su(dA[2], a[ks][2], a0, a1);
+            mma_uu(dB[0], a[ks][0], b0, b1); mma_uu(dB[1], a[ks][1], b0, b1); mma_su(dB[2], a[ks][2], b0, b1);
+        }
+        uint32_t word[2];
+        pack16(dA, dB, t, word);                                // 4 consecutive BYTES of block rows r0 (word 0) and r0 + 8 (word 1)
+        epi.store(pre, 0, r0, strip, word[0]);
+        epi.store(pre, 1, r0 + 8, strip, word[1]);
+    }
+}
+
+// ---- staging: interleaved source -> three byte planes ------------------------------------------------------------------
+// planes[c][row][x]: row pitch PB, plane_rows rows per plane.  A unit = (row, chunk of 4 pixels).
+__device__ __forceinline__ void store_planes(uint8_t* planes, int PB, int plane_rows, int r, int ch, uint32_t R, uint32_t G, uint32_t B) {
+    uint8_t* p = planes + (size_t)r * PB + 4 * ch;
+    *reinterpret_cast<uint32_t*>(p) = R;
+    *reinterpret_cast<uint32_t*>(p + (size_t)plane_rows * PB) = G;
+    *reinterpret_cast<uint32_t*>(p + (size_t)2 * plane_rows * PB) = B;
+}
+
+// 12 interleaved bytes (w0 w1 w2) -> R G B words of 4 pixels
+__device__ __forceinline__ void deinterleave(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t& R, uint32_t& G, uint32_t& B) {
+    R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);      // bytes 0 3 6 9
+    G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);      // bytes 1 4 7 10
+    B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);      // bytes 2 5 8 11
+}
+
+// fp32 source in [0,1] (sampler output): Q1 truncation on the fly.  src -> first float of the staged patch.
+__device__ __forceinline__ void stage_f32(uint8_t* planes, int PB, int plane_rows, const float* __restrict__ src, int64_t pitch_f,
+                                          int rows, int cols) {
+    const int chunks = cols >> 2;
+    for (int i = threadIdx.x; i < rows * chunks; i += kT) {
+        const int r = i / chunks, ch = i - r * chunks;
+        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch_f) + ch * 3;
+        const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2);
+        const uint32_t R = quant_u8(f0.x) | (quant_u8(f0.w) << 8) | (quant_u8(f1.z) << 16) | (quant_u8(f2.y) << 24);
+        const uint32_t G = quant_u8(f0.y) | (quant_u8(f1.x) << 8) | (quant_u8(f1.w) << 16) | (quant_u8(f2.z) << 24);
+        const uint32_t B = quant_u8(f0.z) | (quant_u8(f1.y) << 8) | (quant_u8(f2.x) << 16) | (quant_u8(f2.w) << 24);
+        store_planes(planes, PB, plane_rows, r, ch, R, G, B);
+    }
+}
+
+// u8 interleaved source in global memory (transport payload, canvas without TMA); src 4-byte aligned
+__device__ __forceinline__ void stage_u8(uint8_t* planes, int PB, int plane_rows, const uint8_t* __restrict__ src, int64_t pitch,
+                                         int rows, int cols) {
+    const int chunks = cols >> 2;
+    for (int i = threadIdx.x; i < rows * chunks; i += kT) {
+        const int r = i / chunks, ch = i - r * chunks;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (int64_t)r * pitch) + ch * 3;
+        uint32_t R, G, B;
+        deinterleave(__ldg(p), __ldg(p + 1), __ldg(p + 2), R, G, B);
+        store_planes(planes, PB, plane_rows, r, ch, R, G, B);
+    }
+}
+
+// the same from the two TMA boxes in shared memory (virtual 512-byte rows); lead_b = bytes before the first pixel
+__device__ __forceinline__ void stage_raw(uint8_t* planes, int PB, int plane_rows, const uint8_t* raw, int rows, int cols, int lead_b) {
+    const int chunks = cols >> 2;
+    for (int i = threadIdx.x; i < rows * chunks; i += kT) {
+        const int r = i / chunks, ch = i - r * chunks;
+        uint32_t w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int o = lead_b + 12 * ch + 4 * k;
+            w[k] = *reinterpret_cast<const uint32_t*>(raw + (size_t)(o >> 8) * (kBoxR * kBoxB) + r * kBoxB + (o & 255));
+        }
+        uint32_t R, G, B;
+        deinterleave(w[0], w[1], w[2], R, G, B);
+        store_planes(planes, PB, plane_rows, r, ch, R, G, B);
+    }
+}
+
+template <class Epilogue>
+__device__ __forceinline__ void both_passes(const uint8_t* planes, uint32_t* mid, const int32_t* tabs, const JobView& J, int PB,
+                                            int plane_rows, int bh, Epilogue& epi) {
+    const int steps16 = (J[USDU_J_ROWS] + 15) >> 4;
+    if (J[USDU_J_TAPS_H] <= 1) hpass<1>(planes, mid, tabs, J, PB, plane_rows, steps16);
+    else hpass<2>(planes, mid, tabs, J, PB, plane_rows, steps16);
+    __syncthreads();
+    if (J[USDU_J_TAPS_V] <= 1) vpass<1>(mid, tabs, J, bh, epi);
+    else vpass<2>(mid, tabs, J, bh, epi);
+}
+
+// ======================================================================================
+// crop + resize
+// ======================================================================================
+struct CropEpilogue {
+    float* dst;          // &out[tile][b][oy0][ox0][0]
+    int64_t row_pitch;   // floats per output row
+    int ow3, rows_out;
+    const float* lut;
+    struct Pre {};
+    __device__ __forceinline__ Pre prefetch(int, int, int) const { return Pre{}; }
+    __device__ __forceinline__ void store(const Pre&, int, int r, int strip, uint32_t v) {
+        if (r >= 0 && r < rows_out && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
+            float4 o;
+            o.x = lut[v & 0xFF]; o.y = lut[(v >> 8) & 0xFF]; o.z = lut[(v >> 16) & 0xFF]; o.w = lut[v >> 24];
+            __stcs(reinterpret_cast<float4*>(dst + (int64_t)r * row_pitch + 4 * strip), o);
+        }
+    }
+};
+
+template <bool kTma>
+__global__ void __launch_bounds__(kT, 3)
+crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
+                const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int plane_rows, int mid_rows, int W3,
+                const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job] [lut] [bar] [planes]
+    const size_t region = kTma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
+    uint32_t* mid = reinterpret_cast<uint32_t*>(smem);
+    uint8_t* raw = smem;
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem + region);
+    float* lut = reinterpret_cast<float*>(smem + region + kHeadBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + region + kHeadBytes + 1024);
+    uint8_t* planes = smem + region + kHeadBytes + 1024 + 16;
+    const int PB = plane_pitch(patch_w);
+    pdl_launch_dependents();
+    load_job(job_sm, jobs, blockIdx.x);
+    if (kTma && threadIdx.x == 0) tma::mbar_init(bar, 1);
+    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
+    __syncthreads();
+    const JobView J{job_sm};
+    const int b = blockIdx.y;
+    pdl_wait();                                // the canvas is the previous kernel's output
+    const int sa3 = J[USDU_J_SRC_A] * 3;
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            const int x = sa3 & ~15, y = J[USDU_J_SRC_B];                          // 16-byte aligned box start
+            const bool two = (sa3 - x) + J[USDU_J_COLS] * 3 > kBoxB && x + kBoxB < W3;
+            tma::mbar_expect_tx(bar, (two ? 2 : 1) * kBoxR * kBoxB);
+            tma::load_3d(raw, &cmap, x, y, b, bar);
+            if (two) tma::load_3d(raw + kBoxR * kBoxB, &cmap, x + kBoxB, y, b, bar);
+        }
+        tma::mbar_wait(bar, 0);
+        stage_raw(planes, PB, plane_rows, raw, J[USDU_J_ROWS], J[USDU_J_COLS], sa3 & 15);
+    } else {
+        const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + sa3;
+        stage_u8(planes, PB, plane_rows, src, pitch, J[USDU_J_ROWS], J[USDU_J_COLS]);
+    }
+    __syncthreads();                           // planes complete; raw (aliased with mid) is dead
+    CropEpilogue epi;
+    epi.row_pitch = J[USDU_J_PITCH];
+    epi.dst = out + J.i64(USDU_J_OFF_LO) + (int64_t)b * J.i64(USDU_J_FRAME_LO) + (int64_t)J[USDU_J_DST_Y] * epi.row_pitch +
+              (int64_t)J[USDU_J_DST_X] * 3;
+    epi.ow3 = J[USDU_J_COLS_OUT] * 3;
+    epi.rows_out = J[USDU_J_ROWS_OUT];
+    epi.lut = lut;
+    both_passes(planes, mid, tabs, J, PB, plane_rows, J[USDU_J_CY1], epi);
+}
+
+// ======================================================================================
+// blend
+// ======================================================================================
+struct DTile {
+    uint8_t* base;
+    int bh;                                  // rows per box
+    __device__ __forceinline__ uint32_t* word(int r, int strip) const {
+        const int col = 4 * strip;
+        const int box = col >= kDBox ? 1 : 0;
+        return reinterpret_cast<uint32_t*>(base + (size_t)box * bh * kDBox + r * kDBox + (col - box * kDBox));
+    }
+};
+
+// interior of a tile (alpha == 255 over the whole block): the canvas block becomes S
+struct BlendOpaque {
+    DTile d;
+    int rows;
+    struct Pre {};
+    __device__ __forceinline__ Pre prefetch(int, int, int) const { return Pre{}; }
+    __device__ __forceinline__ void store(const Pre&, int, int r, int strip, uint32_t v) {
+        if (r >= 0 && r < rows) *d.word(r, strip) = v;
+    }
+};
+
+// general case: per-pixel alpha from the feather template, zero outside the tile's sub-rect
+struct BlendFeather {
+    DTile d;
+    const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
+    int mpitch;
+    int cx0, cx1, cy0, cy1;   // sub-rect in block pixel coordinates
+    struct Pre {
+        uint32_t aa[2], ab[2];   // per row half: alpha of the two pixels the 4 bytes touch
+        int split;               // bytes [0, split) belong to the first pixel
+    };
+    __device__ __forceinline__ Pre prefetch(int r0, int r1, int strip) const {
+        const int col = 4 * strip;
+        const int pa = col / 3, pb = (col + 3) / 3;          // pb = pa or pa + 1
+        const bool ina = pa >= cx0 && pa < cx1, inb = pb >= cx0 && pb < cx1;
+        Pre p;
+        p.split = 3 * pb - col;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = h ? r1 : r0;
+            const bool inr = r >= cy0 && r < cy1;
+            const uint8_t* mrow = mask + (int64_t)r * mpitch;
+            p.aa[h] = (inr && ina) ? (uint32_t)__ldg(mrow + pa) : 0u;
+            p.ab[h] = (inr && inb) ? (uint32_t)__ldg(mrow + pb) : 0u;
+        }
+        return p;
+    }
+    __device__ __forceinline__ void store(const Pre& p, int h, int r, int strip, uint32_t v) {
+        const uint32_t aa = p.aa[h], ab = p.ab[h];
+        if ((aa | ab) == 0u) return;                         // also: rows outside [cy0, cy1)
+        uint32_t* w = d.word(r, strip);
+        if ((aa & ab) == 255u) { *w = v; return; }
+        const uint32_t dv = *w;
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a = i < p.split ? aa : ab;
+            o |= composite8((v >> (8 * i)) & 0xFF, (dv >> (8 * i)) & 0xFF, a) << (8 * i);
+        }
+        *w = o;
+    }
+};
+
+template <bool kSrcU8>
+__global__ void __launch_bounds__(kT, 3)
+blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool, const int32_t* __restrict__ jobs,
+                 const void* __restrict__ src_v, int W3, int patch_w, int plane_rows, int mid_rows, int block_rows,
+                 const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // [canvas block: 2 boxes x block_rows x 192] [job] [bar] [planes] [mid]
+    const size_t dbytes = (size_t)2 * block_rows * kDBox;
+    int32_t* job_sm = reinterpret_cast<int32_t*>(smem + dbytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dbytes + kHeadBytes);
+    uint8_t* planes = smem + dbytes + kHeadBytes + 16;
+    uint32_t* mid = reinterpret_cast<uint32_t*>(planes + planes_bytes(patch_w, plane_rows));
+    const int PB = plane_pitch(patch_w);
+    const int b = blockIdx.y;
+    const JobView J{job_sm};
+    DTile D{smem, block_rows};
+    int idx = blockIdx.x;
+    pdl_launch_dependents();
+    load_job(job_sm, jobs, idx);
+    if (threadIdx.x == 0) tma::mbar_init(bar, 1);
+    __syncthreads();
+    pdl_wait();                                // canvas and processed tiles come from earlier kernels
+    const int bx3 = J[USDU_J_DST_X] * 3, by = J[USDU_J_DST_Y];
+    const bool two = bx3 + kDBox < W3;         // the right half exists (a box may not START past the row end)
+    if (threadIdx.x == 0) {                    // canvas block -> shared, asynchronously
+        tma::mbar_expect_tx(bar, (uint32_t)(two ? dbytes : dbytes / 2));
+        tma::load_3d(smem, &cmap, bx3, by, b, bar);
+        if (two) tma::load_3d(smem + (size_t)block_rows * kDBox, &cmap, bx3 + kDBox, by, b, bar);
+    }
+    bool first = true;
+    while (idx >= 0) {
+        if (!first) {
+            __syncthreads();                   // the previous tile's passes are done with job / planes / mid
+            load_job(job_sm, jobs, idx);
+            __syncthreads();
+        }
+        const int64_t first_el = J.i64(USDU_J_SRC_A) + (int64_t)b * J.i64(USDU_J_FRAME_LO);
+        if (kSrcU8)
+            stage_u8(planes, PB, plane_rows, static_cast<const uint8_t*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_COLS]);
+        else
+            stage_f32(planes, PB, plane_rows, static_cast<const float*>(src_v) + first_el, J[USDU_J_PITCH], J[USDU_J_ROWS], J[USDU_J_COLS]);
+        __syncthreads();
+        if (first) tma::mbar_wait(bar, 0);     // the canvas block has landed (before any epilogue touches it)
+        if (J[USDU_J_FLAGS] & 1) {
+            BlendOpaque epi;
+            epi.d = D;
+            epi.rows = J[USDU_J_ROWS_OUT];
+            both_passes(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
+        } else {
+            BlendFeather epi;
+            epi.d = D;
+            epi.mpitch = J[USDU_J_MPITCH];
+            epi.mask = mask_pool + J.i64(USDU_J_OFF_LO);
+            epi.cx0 = J[USDU_J_CX0]; epi.cx1 = J[USDU_J_CX1];
+            epi.cy0 = J[USDU_J_CY0]; epi.cy1 = J[USDU_J_CY1];
+            both_passes(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
+        }
+        idx = J[USDU_J_NEXT];
+        first = false;
+    }
+    tma::fence_async_smem();                   // generic-proxy writes of the block -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::store_3d(&cmap, bx3, by, b, smem);
+        if (two) tma::store_3d(&cmap, bx3 + kDBox, by, b, smem + (size_t)block_rows * kDBox);
+        tma::store_commit();
+        tma::store_wait_read();
+    }
+}
+
+static size_t crop_smem(int patch_w, int plane_rows, int mid_rows, bool use_tma) {
+    const size_t region = use_tma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
+    return region + kHeadBytes + 1024 + 16 + planes_bytes(patch_w, plane_rows);
+}
+static size_t blend_smem(int patch_w, int plane_rows, int mid_rows, int block_rows) {
+    return (size_t)2 * block_rows * kDBox + kHeadBytes + 16 + planes_bytes(patch_w, plane_rows) + mid_bytes(mid_rows);
+}
+
+static int optin(const void* fn, size_t bytes) {
+    if (bytes > 227 * 1024) {
+        set_error("tensor-core kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
+        return USDU_ERR_UNSUPPORTED;
+    }
+    if (bytes > 48 * 1024) USDU_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return USDU_OK;
+}
+
+static int split_patch_h(int patch_h, int* plane_rows, int* mid_rows, const char* who) {
+    *plane_rows = patch_h & 0xFFFF;
+    *mid_rows = (patch_h >> 16) & 0xFFFF;
+    if (*plane_rows <= 0 || *plane_rows % 16 || *mid_rows < *plane_rows || *mid_rows % 4) {
+        set_error("%s: with USDU_FLAG_MMA patch_h carries plane rows (x16) in bits 0..15 and intermediate rows (x4, >= plane rows) "
+                  "in bits 16..31; got %d / %d", who, *plane_rows, *mid_rows);
+        return USDU_ERR_INVALID;
+    }
+    return USDU_OK;
+}
+
+int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
+                int patch_w, int patch_h, float* out, cudaStream_t st) {
+    int plane_rows, mid_rows;
+    int s = split_patch_h(patch_h, &plane_rows, &mid_rows, "usdu_tile_crop_resize");
+    if (s != USDU_OK) return s;
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    // TMA staging needs the patch to fit the two boxes (the planner keeps the staged rows <= 48 for scales <= ~1.2)
+    bool use_tma = plane_rows <= kBoxR && 12 + patch_w * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
+    if (use_tma) use_tma = tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kBoxB, kBoxR);
+    const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, use_tma);
+    const void* fn = use_tma ? (const void*)crop_mma_kernel<true> : (const void*)crop_mma_kernel<false>;
+    s = optin(fn, smem);
+    if (s != USDU_OK) return s;
+    if (use_tma)
+        USDU_CUDA(launch_pdl(crop_mma_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W * 3, cmap));
+    else
+        USDU_CUDA(launch_pdl(crop_mma_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W * 3, cmap));
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
+                 const int32_t* items, int n_items, int patch_w, int patch_h, const void* src, int src_is_u8, int block_rows,
+                 cudaStream_t st) {
+    if (block_rows != 16 && block_rows != 32) {
+        set_error("usdu_tile_blend: the tensor-core path needs a block height of 16 or 32 in flags bits 8..15, got %d", block_rows);
+        return USDU_ERR_INVALID;
+    }
+    int plane_rows, mid_rows;
+    int s = split_patch_h(patch_h, &plane_rows, &mid_rows, "usdu_tile_blend");
+    if (s != USDU_OK) return s;
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    if (((uintptr_t)canvas & 15) != 0 ||
+        !tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kDBox, block_rows)) {
+        set_error("usdu_tile_blend: cannot build the canvas tensor map (cuTensorMapEncodeTiled)");
+        return USDU_ERR_CUDA;
+    }
+    const size_t smem = blend_smem(patch_w, plane_rows, mid_rows, block_rows);
+    const void* fn = src_is_u8 ? (const void*)blend_mma_kernel<true> : (const void*)blend_mma_kernel<false>;
+    s = optin(fn, smem);
+    if (s != USDU_OK) return s;
+    if (src_is_u8)
+        USDU_CUDA(launch_pdl(blend_mma_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, plane_rows, mid_rows, block_rows, cmap));
+    else
+        USDU_CUDA(launch_pdl(blend_mma_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, plane_rows, mid_rows, block_rows, cmap));
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+}  // namespace mma
+}  // namespace usdu

@@ -84,11 +84,13 @@ def tile_payload_layout(plan, assignment: Sequence[Sequence[int]], B: int):
 # offset, which the blend kernel's 64-bit source offsets already express.
 # --------------------------------------------------------------------------------------
 USE_PEER_BLEND = os.environ.get("USDU_PEER_BLEND", "1") != "0"
-# ... and, with it, the final blend itself is shared out: the master's canvas is a symmetric
-# allocation too, every rank composites its share of the canvas BLOCKS (all worker tiles, ascending
-# id, same order inside every block) straight into the master's HBM, reading the tiles from their
-# owners' HBM.  Blocks are owned by exactly one CTA of exactly one rank, so the result is the one
-# the single launch on the master produces.
+# ... and, with it, the final composite is SHARDED BY CANVAS SLAB: every rank owns one horizontal slab of the final
+# canvas (whole block rows), quantises it from the input, composites every tile that reaches into it -- the master's
+# tiles in the master's order, then all worker tiles in ascending id, the order of static.py:521-553 inside every
+# block -- into its LOCAL HBM (bulk-tensor loads and stores never leave the device; only the u8 tiles are read from
+# their owners over NVLink), and the master gathers the N finished slabs with peer LOADS while it dequantises them
+# into the result.  (Round 1 let every rank store its blocks into the master's canvas: N-1 ranks storing into one
+# HBM with a system-scope fence per CTA made N = 8 slower than N = 2.)
 USE_SHARED_FINAL_BLEND = os.environ.get("USDU_SHARED_FINAL_BLEND", "1") != "0"
 
 
@@ -103,6 +105,7 @@ class PeerPayload:
     """Symmetric u8 buffer + rendezvous handle, cached per (tag, bytes, device, group)."""
 
     _cache: Dict[tuple, Optional["PeerPayload"]] = {}
+    _warned = False
 
     def __init__(self, nbytes: int, device, group):
         import torch.distributed._symmetric_memory as symm
@@ -116,6 +119,10 @@ class PeerPayload:
         release/acquire): kernels enqueued before it on any rank are complete and visible to
         kernels enqueued after it on every rank."""
         self.hdl.barrier(channel=channel, timeout_ms=20000)
+
+    def peer_view(self, rank: int, shape, dtype=torch.uint8) -> torch.Tensor:
+        """Rank `rank`'s buffer as a tensor mapped into this process (NVLink peer memory)."""
+        return self.hdl.get_buffer(rank, tuple(shape), dtype)
 
     @classmethod
     def get(cls, nbytes: int, device, group, tag: str = "payload") -> Optional["PeerPayload"]:
@@ -136,6 +143,12 @@ class PeerPayload:
         td.all_reduce(flag, op=td.ReduceOp.MIN, group=group)
         if int(flag.item()) == 0:
             obj = None
+            if not cls._warned:        # once: a mis-set box must not lose the NVLink transport silently
+                cls._warned = True
+                import warnings
+                warnings.warn("comfyui-distributed_b200: symmetric-memory peer transport unavailable "
+                              f"({cls.last_error or 'a peer rank failed'}); falling back to NCCL all_gather of the tiles",
+                              RuntimeWarning, stacklevel=2)
         if len(cls._cache) > 8:
             cls._cache.clear()
         cls._cache[key] = obj
@@ -153,6 +166,117 @@ def final_blend_order(assignment: Sequence[Sequence[int]]) -> List[int]:
 # --------------------------------------------------------------------------------------
 # static mode, SPMD
 # --------------------------------------------------------------------------------------
+class StaticJob:
+    """Everything one rank needs for static-mode jobs of one geometry: the plan and its partition, the symmetric
+    buffers (u8 tile payload, working canvas, final canvas), the captured per-rank wave graph and the slab of the
+    final canvas this rank composites.  Cached: a second job of the same shape only replays."""
+
+    _cache: Dict[tuple, "StaticJob"] = {}
+
+    def __init__(self, plan, B: int, device, group, denoiser, assignment, graphed: bool):
+        from . import engine as _eng
+        from .engine import Canvas, DevicePlan
+        self.plan, self.B, self.device, self.group = plan, B, device, group
+        self.rank, self.world = dist_info(group)
+        world = self.world
+        self.asg = [list(a) for a in (assignment if assignment is not None else plan.partition(world))]
+        if len(self.asg) != world:
+            raise ValueError(f"assignment has {len(self.asg)} participants, world size is {world}")
+        self.dp = DevicePlan.get(plan, device)
+        self.conflict_free = plan.conflict_free(self.asg)
+        # payload layout follows every rank's processing order (wave by wave), so a wave's packed u8 tiles land in
+        # one contiguous span
+        proc = [_eng.processing_order(plan, a) for a in self.asg]
+        self.where, sizes = tile_payload_layout(plan, proc, B)
+        self.sizes = [max(sz, 16) for sz in sizes]
+        pitch = Canvas.pitch_of(plan.W)
+        self.canvas_bytes = B * plan.H * pitch
+        self.peer = PeerPayload.get((max(self.sizes) + 255) // 256 * 256, device, group) if world > 1 else None
+        self.work = self.final = None
+        if self.peer is not None and USE_SHARED_FINAL_BLEND:
+            self.work = PeerPayload.get(self.canvas_bytes, device, group, tag="work")
+            self.final = PeerPayload.get(self.canvas_bytes, device, group, tag="final")
+        self.sharded = self.final is not None and self.work is not None
+        if world > 1:
+            self.payload = (self.peer.buf[: self.sizes[self.rank]] if self.peer is not None
+                            else _payload_buffer(self.sizes[self.rank], device))
+        else:
+            self.payload = None
+        self.work_buf = self.work.buf[: self.canvas_bytes].view(B, plan.H, pitch) if self.sharded else None
+        # the composite order of the final canvas: the master's tiles as the master processed them, then every
+        # worker tile in ascending id (static.py:521-553)
+        self.final_order = list(self.asg[0]) + final_blend_order(self.asg)
+        self.graphed = graphed and len(self.asg[self.rank]) > 0
+        # with a conflict-free partition no crop of this rank ever sees one of its own blends and, when the final
+        # canvas is composited slab by slab from the payloads, nobody reads this rank's working canvas: skip them
+        self.skip = ("blend",) if (self.sharded and self.conflict_free) else ()
+        self.gw = None
+        if self.graphed:
+            self.gw = _eng.GraphedWaves.get(self.dp, B, denoiser, _eng.PROFILE, order=self.asg[self.rank], payload=self.payload,
+                                            where=self.where, canvas_buf=self.work_buf, skip=self.skip)
+        self.final_canvas = None
+        self.rows = None
+        if self.sharded:
+            self.final_canvas = Canvas(self.dp, B, self.final.buf[: self.canvas_bytes].view(B, plan.H, pitch))
+            offs = peer_offsets(self.final_order, self.where, self.peer.ptrs, self.rank)
+            wl = self.dp.blend_list(tuple(self.final_order), offs, True, self.final_canvas.path, B, (self.rank, world))[0]
+            self.final_offs = offs
+            bh = max(wl.block_rows, 1)
+            nby = (plan.H + bh - 1) // bh
+            self.rows = [(min((nby * q) // world * bh, plan.H), min((nby * (q + 1)) // world * bh, plan.H)) for q in range(world)]
+            assert self.rows[self.rank] == tuple(wl.rows), (self.rows, wl.rows)
+
+    @classmethod
+    def get(cls, plan, B, device, group, denoiser, assignment, graphed: bool) -> "StaticJob":
+        from . import engine as _eng
+        akey = None if assignment is None else tuple(tuple(a) for a in assignment)
+        key = (id(plan), B, str(device), id(group), getattr(denoiser, "graph_key", id(denoiser)) if graphed else "eager",
+               akey, graphed, _eng.FORCE_GENERIC, _eng.FORCE_NO_MMA, USE_PEER_BLEND, USE_SHARED_FINAL_BLEND)
+        job = cls._cache.get(key)
+        if job is None or job.plan is not plan:
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            job = cls._cache[key] = StaticJob(plan, B, device, group, denoiser, assignment, graphed)
+        return job
+
+    # ---- phases -----------------------------------------------------------------------------
+    def run_tiles(self, image: Optional[torch.Tensor], denoiser, resident: bool = False):
+        """Phase A: this rank's tiles (crop -> sampler -> local blend -> u8 pack into the payload).  resident: the
+        working canvas already holds the quantised input (host path: gathered slabs)."""
+        from .engine import Canvas, run_progressive
+        if self.gw is not None:
+            return self.gw.replay(image) if not resident else self.gw.replay_resident()
+        canvas = Canvas(self.dp, self.B, self.work_buf)
+        if not resident:
+            canvas.load(image)
+        run_progressive(canvas, self.asg[self.rank], denoiser, payload=self.payload, where=self.where, skip=self.skip)
+        return canvas
+
+    def composite_slab(self, image_ptr: int, frame_stride_rows: Optional[int] = None):
+        """Phase B: this rank's slab of the final canvas = quantised input rows + every tile, in the reference's order.
+        image_ptr: address of row 0 of frame 0 of the fp32 input as THIS process sees it (a slab upload passes an
+        address offset so that its first row lands on the slab's first row)."""
+        from . import _native as nat
+        from .engine import _stream_ptr
+        p, c = self.plan, self.final_canvas
+        y0, y1 = self.rows[self.rank]
+        if y1 > y0:
+            nat.quantize_rows(image_ptr, c.buf.data_ptr(), self.B, p.H, p.W, c.pitch, y0, y1, _stream_ptr())
+            c.launches += 1
+        c.blend(self.final_order, self.peer.buf, self.final_offs, part=(self.rank, self.world))
+
+    def gather_result(self, out: torch.Tensor):
+        """Phase C on the producing rank: dequantise the N finished slabs straight out of their owners' HBM."""
+        from . import _native as nat
+        from .engine import _stream_ptr
+        p, c = self.plan, self.final_canvas
+        for q in range(self.world):
+            y0, y1 = self.rows[q]
+            if y1 > y0:
+                nat.dequantize_rows(self.final.ptrs[q], out.data_ptr(), self.B, p.H, p.W, c.pitch, y0, y1, _stream_ptr())
+                c.launches += 1
+
+
 def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int,
                    mask_blur: int, force_uniform_tiles: bool = True, group=None,
                    assignment: Optional[Sequence[Sequence[int]]] = None, all_ranks_result: bool = False,
@@ -160,79 +284,269 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
     """Every rank calls this with the same (replicated) CUDA image, like the reference's
     workers which each re-execute the upstream graph.  Rank 0 returns the
     blended canvas; other ranks return `image` unchanged unless all_ranks_result."""
-    from . import _native as nat
-    from .engine import Canvas, DevicePlan, _require_cuda, _stream_ptr, run_progressive
+    from . import engine as _eng
+    from .engine import Canvas, _require_cuda
     from .planner import get_plan
 
     _require_cuda(image, "image")
     rank, world = dist_info(group)
     B, H, W, _ = image.shape
     plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
-    asg = [list(a) for a in (assignment if assignment is not None else plan.partition(world))]
-    if len(asg) != world:
-        raise ValueError(f"assignment has {len(asg)} participants, world size is {world}")
+    image = image.contiguous()
     with torch.cuda.device(image.device):
-        dp = DevicePlan.get(plan, image.device)
-        from . import engine as _eng
-        # payload layout follows every rank's processing order (wave by wave), so a wave's
-        # packed u8 tiles land in one contiguous span
-        proc = [_eng.processing_order(plan, a) for a in asg]
-        where, sizes = tile_payload_layout(plan, proc, B)
-        sizes = [max(sz, 16) for sz in sizes]
-        graphed = (bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS and not all_ranks_result
-                   and len(asg[rank]) > 0)          # a participant without tiles has nothing to capture
-        payload = None
-        peer = PeerPayload.get((max(sizes) + 255) // 256 * 256, image.device, group) if world > 1 else None
-        shared = None     # symmetric canvases: every rank can composite into the master's
-        if peer is not None and USE_SHARED_FINAL_BLEND and not all_ranks_result:
-            shared = PeerPayload.get(B * H * Canvas.pitch_of(W), image.device, group, tag="canvas")
-        cbuf = shared.buf.view(B, H, Canvas.pitch_of(W)) if shared is not None else None
-        if world > 1:
-            payload = (peer.buf[: sizes[rank]] if peer is not None
-                       else _payload_buffer(sizes[rank], image.device))
-        if graphed:      # this rank's wave loop (crop -> sampler -> local blend -> u8 pack) as one CUDA graph
-            gw = _eng.GraphedWaves.get(dp, B, denoiser, _eng.PROFILE, order=asg[rank], payload=payload, where=where,
-                                       canvas_buf=cbuf)
-            canvas, base = gw.replay(image), None
-        else:
-            canvas = Canvas(dp, B, cbuf).load(image)
-            base = canvas.clone() if (all_ranks_result and rank != 0) else None
-            run_progressive(canvas, asg[rank], denoiser, payload=payload, where=where)
-        if world > 1:
-            produce_here = rank == 0 or all_ranks_result
-            target, order = canvas, final_blend_order(asg)
-            if produce_here and rank != 0:
-                # rebuild the master's canvas: base + master tiles in the master's order
-                target, order = base, list(asg[0]) + order
-            if shared is not None:
-                peer.barrier(0)                          # every payload is complete, the master's own tiles are blended
-                canvas.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank), part=(rank, world),
-                             canvas_ptr=shared.ptrs[0])
-                peer.barrier(1)                          # every share has landed in the master's canvas
-            elif peer is not None:
-                peer.barrier(0)                          # every payload is complete and visible
-                if produce_here:
-                    target.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank))
-                peer.barrier(1)                          # nobody refills its payload while it is being read
-            else:
-                gathered, _ = all_gather_bytes(payload, group, sizes=sizes)
-                cap = gathered.shape[1]
-                if produce_here:
-                    offs = np.array([where[t][0] * cap + where[t][1] for t in order], dtype=np.int64)
-                    target.blend(order, gathered.view(-1), offs)
-            if produce_here:
-                canvas = target
+        graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS
+        job = StaticJob.get(plan, B, image.device, group, denoiser, assignment, graphed)
+        asg, where, peer = job.asg, job.where, job.peer
         produce = rank == 0 or all_ranks_result
-        res = canvas.result() if produce else image
+        if job.sharded:
+            marks = [] if (stats is not None and stats.get("time_phases")) else None
+
+            def mark(name):                              # per-rank phase times (bench.py reports the max over ranks)
+                if marks is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    marks.append((name, e))
+
+            mark("start")
+            canvas = job.run_tiles(image, denoiser)
+            mark("tiles (quantise + crop/sampler/blend waves + pack)")
+            peer.barrier(0)                              # every payload is complete and visible
+            mark("barrier 0")
+            job.final_canvas.launches = job.final_canvas.algo_bytes = 0
+            job.composite_slab(image.data_ptr())
+            mark("composite own slab of the final canvas")
+            peer.barrier(1)                              # every slab is final; nobody refills a payload that is being read
+            mark("barrier 1")
+            res = image
+            if produce:
+                res = torch.empty((B, H, W, 3), dtype=torch.float32, device=image.device)
+                job.gather_result(res)
+            mark("gather + dequantise the slabs (producing rank)")
+            if marks is not None:
+                torch.cuda.current_stream().synchronize()
+                stats["phase_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+            launches = canvas.launches + job.final_canvas.launches
+            algo = canvas.algo_bytes + job.final_canvas.algo_bytes
+        else:
+            base = None
+            if job.gw is not None and not all_ranks_result:
+                canvas = job.gw.replay(image)
+            else:
+                canvas = Canvas(job.dp, B).load(image)
+                base = canvas.clone() if (all_ranks_result and rank != 0) else None
+                _eng.run_progressive(canvas, asg[rank], denoiser, payload=job.payload, where=where)
+            if world > 1:
+                target, order = canvas, final_blend_order(asg)
+                if produce and rank != 0:
+                    # rebuild the master's canvas: base + master tiles in the master's order
+                    target, order = base, list(asg[0]) + order
+                if peer is not None:
+                    peer.barrier(0)                          # every payload is complete and visible
+                    if produce:
+                        target.blend(order, peer.buf, peer_offsets(order, where, peer.ptrs, rank))
+                    peer.barrier(1)                          # nobody refills its payload while it is being read
+                else:
+                    gathered, _ = all_gather_bytes(job.payload, group, sizes=job.sizes)
+                    cap = gathered.shape[1]
+                    if produce:
+                        offs = np.array([where[t][0] * cap + where[t][1] for t in order], dtype=np.int64)
+                        target.blend(order, gathered.view(-1), offs)
+                if produce:
+                    canvas = target
+            res = canvas.result() if produce else image
+            launches, algo = canvas.launches, canvas.algo_bytes
     if stats is not None:
-        stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches
-        stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes
+        stats["gpu_launches"] = stats.get("gpu_launches", 0) + launches
+        stats["algo_bytes"] = stats.get("algo_bytes", 0) + algo
         stats["tiles"] = len(plan.tiles)
         stats["tiles_this_rank"] = len(asg[rank])
-        stats["conflict_free"] = plan.conflict_free(asg)
+        stats["conflict_free"] = job.conflict_free
         stats["transport"] = "single" if world == 1 else ("nvlink peer loads" if peer is not None else "nccl all_gather")
-        stats["final_blend"] = "master" if shared is None else f"shared by {world} ranks (peer stores into the master's canvas)"
+        stats["final_blend"] = ("master" if not job.sharded else
+                                f"sharded: each of {world} ranks composites its slab of the final canvas locally, the master gathers the slabs")
     return res
+
+
+# --------------------------------------------------------------------------------------
+# static mode on HOST tensors: every rank moves 1/N of the image over ITS OWN PCIe link
+# --------------------------------------------------------------------------------------
+class SharedHost:
+    """Result buffers in POSIX shared memory, page-locked (cudaHostRegister) in every rank's process, plus a small
+    control block for host-side hand-shakes.  The reference's workers each hold the whole canvas and the master alone
+    returns the result (upscale/modes/static.py:209-212, :556-564); here every rank downloads its slab of the final
+    canvas into the master's result tensor directly, so no result byte crosses NVLink or the master's PCIe link."""
+
+    _inst: Dict[int, "SharedHost"] = {}
+    CTRL_WORDS = 64 + 64          # [0] job id published by rank 0, [1] buffer index of that job, [64 + r] last job rank r finished
+
+    def __init__(self, group):
+        import atexit
+        import uuid
+        self.group = group
+        self.rank, self.world = dist_info(group)
+        tok = [f"{os.getpid()}_{uuid.uuid4().hex[:10]}" if self.rank == 0 else None]
+        td.broadcast_object_list(tok, src=td.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.uid = tok[0]
+        self.paths: List[str] = []
+        path = self._path("ctrl")
+        if self.rank == 0:
+            np.zeros(self.CTRL_WORDS, dtype=np.int64).tofile(path)
+            self.paths.append(path)
+        td.barrier(group=group)
+        self.ctrl = np.memmap(path, dtype=np.int64, mode="r+", shape=(self.CTRL_WORDS,))
+        self.job = 0
+        self.bufs: Dict[tuple, List[torch.Tensor]] = {}     # (nbytes) -> mapped + registered tensors by index
+        atexit.register(self.close)
+
+    @classmethod
+    def get(cls, group) -> "SharedHost":
+        key = id(group)
+        if key not in cls._inst:
+            cls._inst[key] = SharedHost(group)
+        return cls._inst[key]
+
+    def _path(self, name: str) -> str:
+        return f"/dev/shm/usdu_b200_{self.uid}_{name}"
+
+    def close(self):
+        for p in self.paths:
+            try:
+                os.unlink(p)
+            except OSError:
+                pass
+        self.paths = []
+
+    def _map(self, numel: int, k: int) -> torch.Tensor:
+        """Buffer k of `numel` floats: mapped and page-locked on first use (~150 ms for 400 MB, once)."""
+        lst = self.bufs.setdefault(numel, [])
+        while len(lst) <= k:
+            lst.append(None)
+        if lst[k] is None:
+            path = self._path(f"{numel}_{k}")
+            if self.rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(numel * 4)
+                self.paths.append(path)
+            t = torch.from_file(path, shared=True, size=numel, dtype=torch.float32)
+            err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * 4, 0)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared result buffer failed: {err}")
+            lst[k] = t
+        return lst[k]
+
+    def _wait(self, idx: int, value: int, what: str):
+        import time
+        t0 = time.perf_counter()
+        while int(self.ctrl[idx]) < value:
+            if time.perf_counter() - t0 > 120.0:
+                raise RuntimeError(f"shared-host hand-shake timed out waiting for {what}")
+
+    def begin(self, shape) -> torch.Tensor:
+        """Collective (host side only): the result tensor of the next job, the same physical pages on every rank.
+        Rank 0 picks a buffer nobody references any more (engine.buffer_is_unreferenced) or maps a new one."""
+        from .engine import buffer_is_unreferenced
+        numel = int(np.prod(shape))
+        self.job += 1
+        if self.rank == 0:
+            lst = self.bufs.setdefault(numel, [])
+            have = len(lst)
+            k = have                           # (index loop: a loop variable bound to the tensor would count as a reference)
+            for i in range(have):
+                if lst[i] is not None and buffer_is_unreferenced(lst[i]):
+                    k = i
+                    break
+            buf = self._map(numel, k)          # the file exists before the index is published
+            if k < have and torch.cuda.is_available():
+                torch.cuda.synchronize()       # copies a consumer may have queued out of a recycled buffer
+            self.ctrl[1] = k
+            self.ctrl[0] = self.job
+        else:
+            self._wait(0, self.job, "the master to publish the job")
+            buf = self._map(numel, int(self.ctrl[1]))
+        return buf.view(tuple(shape))
+
+    def finish(self):
+        """This rank's part of the result has landed (call after synchronising the copy stream); rank 0 returns once
+        every rank's part has."""
+        self.ctrl[64 + self.rank] = self.job
+        if self.rank == 0:
+            for r in range(self.world):
+                self._wait(64 + r, self.job, f"rank {r}'s slab")
+
+
+def upscale_static_host(host_image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int, mask_blur: int,
+                        force_uniform_tiles: bool = True, group=None, device: Optional[torch.device] = None,
+                        stats: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """Static mode for HOST images (what ComfyUI hands the node; every rank holds the same image because every rank
+    re-executed the upstream graph).  Rank r uploads only slab r -- 1/N of the rows, over its own PCIe
+    link -- and quantises it; the u8 slabs are exchanged over NVLink (a quarter of the fp32 bytes); the tiles run as in
+    upscale_static; every rank composites its slab of the final canvas, dequantises it and downloads it into ONE result
+    tensor in page-locked shared memory.  Returns that tensor on rank 0 and None on the other ranks; falls back to
+    upload-everything + upscale_static when the NVLink peer transport is unavailable (returns NotImplemented)."""
+    from . import _native as nat
+    from . import engine as _eng
+    from .engine import _stream_ptr
+    from .planner import get_plan
+
+    rank, world = dist_info(group)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    x = host_image.to(torch.float32).contiguous()
+    B, H, W, _ = x.shape
+    plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
+    with torch.cuda.device(device):
+        graphed = bool(getattr(denoiser, "cuda_graph_safe", False)) and _eng.USE_CUDA_GRAPHS
+        job = StaticJob.get(plan, B, device, group, denoiser, None, graphed)
+        if not job.sharded:
+            return NotImplemented
+        shared = SharedHost.get(group)
+        out = shared.begin((B, H, W, 3))
+        y0, y1 = job.rows[rank]
+        n = y1 - y0
+        max_rows = max(b - a for a, b in job.rows)
+        if getattr(job, "slab", None) is None:
+            job.slab = torch.empty((B, max(max_rows, 1), W, 3), dtype=torch.float32, device=device)
+            job.stage = None
+        slab, work, fin = job.slab, job.work_buf, job.final_canvas
+        pitch, row_bytes = fin.pitch, W * 3 * 4
+        src = x
+        if n > 0 and not x.is_pinned():            # pageable input: only this rank's slab goes through a pinned staging buffer
+            if job.stage is None:
+                job.stage = torch.empty((B, max(max_rows, 1), W, 3), dtype=torch.float32, pin_memory=True)
+            job.stage[:, :n].copy_(x[:, y0:y1])
+            src = None
+        for b in range(B):                             # H2D of the slab, one contiguous span per frame
+            if n > 0:
+                slab[b, :n].copy_(job.stage[b, :n] if src is None else x[b, y0:y1], non_blocking=True)
+                # `slab[b]` holds rows y0..y1 of frame b: hand the kernel the address its row 0 would have
+                nat.quantize_rows(slab[b].data_ptr() - y0 * row_bytes, work[b].data_ptr(), 1, H, W, pitch, y0, y1, _stream_ptr())
+        job.peer.barrier(0)                            # every slab of the quantised input is in its owner's working canvas
+        for q in range(world):                         # all-gather of the u8 slabs: peer loads over NVLink
+            a, b_ = job.rows[q]
+            if q != rank and b_ > a:
+                work[:, a:b_].copy_(job.work.peer_view(q, (B, H, pitch))[:, a:b_], non_blocking=True)
+        job.peer.barrier(1)                            # nobody blends into a working canvas that is still being read
+        canvas = job.run_tiles(None, denoiser, resident=True)
+        job.peer.barrier(0)                            # every payload is complete and visible
+        fin.launches = fin.algo_bytes = 0
+        for b in range(B):
+            if n > 0:
+                nat.quantize_rows(slab[b].data_ptr() - y0 * row_bytes, fin.buf[b].data_ptr(), 1, H, W, pitch, y0, y1, _stream_ptr())
+        fin.blend(job.final_order, job.peer.buf, job.final_offs, part=(rank, world))
+        job.peer.barrier(1)                            # nobody refills a payload that is still being read
+        for b in range(B):
+            if n > 0:
+                nat.dequantize_rows(fin.buf[b].data_ptr(), slab[b].data_ptr() - y0 * row_bytes, 1, H, W, pitch, y0, y1, _stream_ptr())
+                out[b, y0:y1].copy_(slab[b, :n], non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        shared.finish()
+    if stats is not None:
+        stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches + fin.launches + 3 * B
+        stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes + fin.algo_bytes
+        stats["tiles"], stats["tiles_this_rank"] = len(plan.tiles), len(job.asg[rank])
+        stats["conflict_free"] = job.conflict_free
+        stats["transport"] = "nvlink peer loads"
+        stats["host_path"] = f"slab {rank}: rows {y0}-{y1} of {H} up and down over this rank's PCIe link"
+    return out if rank == 0 else None
 
 
 _PAYLOADS: Dict[tuple, torch.Tensor] = {}

@@ -69,6 +69,7 @@ class KernelProfile:
 
 PROFILE: Optional[KernelProfile] = None
 FORCE_GENERIC = False     # tests: run the generic (any-scale) kernels even when the fast ones apply
+FORCE_NO_MMA = os.environ.get("USDU_NO_MMA", "0") == "1"   # tests / A-B runs: integer-pipe fast kernels instead of the tensor-core ones
 USE_CUDA_GRAPHS = True    # capture the wave loop when the sampler is cuda_graph_safe
 
 
@@ -142,7 +143,8 @@ class Canvas:
         self.buf = buf                      # caller-owned when given (dist.py: symmetric memory peers can address)
         self.launches = 0
         self.algo_bytes = 0
-        self.flags = nat.FLAG_FAST if (self.plan.fast and not FORCE_GENERIC) else 0
+        self.path = 0 if FORCE_GENERIC else self.plan.kernel_path(1 if FORCE_NO_MMA else None)   # 0 generic, 1 fast, 2 tensor-core
+        self.flags = (0, nat.FLAG_FAST, nat.FLAG_MMA)[self.path]
         self.share = 1                      # launches expected to run side by side (tile-granular schedule)
 
     @staticmethod
@@ -184,7 +186,7 @@ class Canvas:
         """-> (flat fp32 buffer, element offsets per tile).  Tile i is
         buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
         tile_ids = tuple(int(t) for t in tile_ids)
-        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, bool(self.flags & nat.FLAG_FAST), self.share)
+        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, self.path, self.share)
         if out is None:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
@@ -211,7 +213,7 @@ class Canvas:
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, bool(self.flags & nat.FLAG_FAST), self.B, part,
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, self.path, self.B, part,
                                               1 if part is not None else self.share)
         if items.shape[0] == 0:
             return
@@ -444,7 +446,7 @@ class GraphedWaves:
             canvas_buf: Optional[torch.Tensor] = None) -> "GraphedWaves":
         pkey = None if payload is None else (payload.data_ptr(), payload.numel())
         ckey = None if canvas_buf is None else canvas_buf.data_ptr()
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, SCHEDULE,
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE,
                None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
@@ -459,6 +461,13 @@ class GraphedWaves:
         c = self.canvas
         c.launches, c.algo_bytes = self.launches_per_replay, self.bytes_per_replay
         c.load(image)
+        self.graph.replay()
+        return c
+
+    def replay_resident(self) -> Canvas:
+        """The captured wave loop on a canvas the caller has already filled with the quantised input."""
+        c = self.canvas
+        c.launches, c.algo_bytes = self.launches_per_replay, self.bytes_per_replay
         self.graph.replay()
         return c
 
@@ -548,7 +557,7 @@ class HostPipeline:
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, n_bands: int) -> "HostPipeline":
         graph_safe = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
         # a captured pipeline belongs to one sampler configuration; an eager one serves any sampler
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)) if graph_safe else "eager", n_bands, FORCE_GENERIC)
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)) if graph_safe else "eager", n_bands, FORCE_GENERIC, FORCE_NO_MMA)
         hp = cls._cache.get(key)
         if hp is None or hp.dp is not dp:
             if len(cls._cache) > 2:
@@ -655,18 +664,34 @@ class _PinnedPool:
         self.keep = keep
 
     def get(self, shape, dtype=torch.float32) -> torch.Tensor:
-        import sys
         key = (tuple(shape), dtype)
         lst = self.bufs.setdefault(key, [])
         for i in range(len(lst)):
-            # the list + getrefcount's own argument; the tensor + the temporary storage wrapper
-            if sys.getrefcount(lst[i]) <= 2 and torch._C._storage_Use_Count(lst[i].untyped_storage()._cdata) <= 2:
+            if buffer_is_unreferenced(lst[i]):
+                # a consumer may have queued an asynchronous copy out of the buffer on some stream and dropped the
+                # tensor right away: let everything in flight on the device finish before the buffer is rewritten
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
                 return lst[i]
         if len(lst) >= self.keep:
             lst.pop(0)                               # still referenced elsewhere: just forget it
         t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         lst.append(t)
         return t
+
+
+def buffer_is_unreferenced(t: torch.Tensor) -> bool:
+    """True when nothing but the caller's container references tensor `t` or its storage: no other Python reference
+    to the tensor object (views hold one through `_base`) and no other owner of the storage (numpy arrays made with
+    `.numpy()` and views own the storage without referencing the tensor).  The storage count comes from a private torch
+    entry point; when a torch build lacks it the answer is always False -- buffers are then never recycled, only
+    replaced (slower, never unsafe)."""
+    import sys
+    use_count = getattr(torch._C, "_storage_Use_Count", None)
+    if use_count is None:
+        return False
+    # the container + getrefcount's own argument (+ this function's parameter); the tensor + the temporary wrapper
+    return sys.getrefcount(t) <= 3 and use_count(t.untyped_storage()._cdata) <= 2
 
 
 PINNED_RESULTS = _PinnedPool()

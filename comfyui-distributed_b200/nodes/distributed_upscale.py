@@ -107,6 +107,15 @@ class UltimateSDUpscaleDistributed:
         src_device = upscaled_image.device
         dev = src_device if upscaled_image.is_cuda else torch.device("cuda", torch.cuda.current_device())
         self.last_stats = {}
+        if multi_job_id and is_worker and world == 1:
+            # The reference's HTTP orchestrator started this process as a worker (static.py:191-314).  Its tile queue
+            # and PNG transport are not part of this package (an SPMD launch, one rank per GPU, replaces them): do what
+            # a worker does for the graph -- hand the input through (static.py:314) -- and say why no tile was processed.
+            import warnings
+            warnings.warn("UltimateSDUpscaleDistributed (B200): running as an HTTP worker of the reference's orchestrator is "
+                          "not supported; launch one rank per GPU with torch.distributed instead. Returning the input.",
+                          RuntimeWarning, stacklevel=2)
+            return (upscaled_image,)
         if not upscaled_image.is_cuda and not distributed:
             # ComfyUI IMAGE tensors live on the host: upload, kernels and download overlap band by band
             _, H, W, _ = upscaled_image.shape
@@ -114,6 +123,15 @@ class UltimateSDUpscaleDistributed:
                                            denoise, tiled_decode, (W, H))
             return (upscale_host(upscaled_image, denoiser, tile_width, tile_height, padding, mask_blur,
                                  force_uniform_tiles, device=dev, stats=self.last_stats),)
+        if distributed and not upscaled_image.is_cuda:
+            # every rank moves only its slab of the image over its own PCIe link (dist.upscale_static_host)
+            _, H, W, _ = upscaled_image.shape
+            denoiser = self._make_denoiser(model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler,
+                                           denoise, tiled_decode, (W, H))
+            out = usdu_dist.upscale_static_host(upscaled_image, denoiser, tile_width, tile_height, padding, mask_blur,
+                                                force_uniform_tiles, device=dev, stats=self.last_stats)
+            if out is not NotImplemented:
+                return (upscaled_image,) if worker else (out,)
         if upscaled_image.is_cuda:
             image = upscaled_image.to(torch.float32)
         else:

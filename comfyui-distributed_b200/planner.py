@@ -106,6 +106,62 @@ def _overlap(a: Tuple[int, int, int, int], b: Tuple[int, int, int, int]) -> bool
 
 
 # --------------------------------------------------------------------------------------
+# tensor-core fragments of a resample table (csrc/usdu_mma.cu)
+# --------------------------------------------------------------------------------------
+MMA_M = 16                 # outputs per M-tile (mma.sync.m16n8k32)
+MMA_K = 32                 # inputs per k-step
+MMA_MAX_KSTEPS = 2
+
+
+def build_mma_frags(tab: np.ndarray) -> Optional[np.ndarray]:
+    """A resampling axis as a banded matrix product on the tensor cores: out[o] = sum_k A[o][k] * in[k0 + k] with the
+    22-bit fixed-point coefficients of Pillow (tab = header + bounds + kk of usdu_build_resample_table) split into three
+    8-bit limbs, coef = l2 * 65536 + l1 * 256 + l0 (l0, l1 unsigned, l2 signed), one u8 x u8 / s8 x u8 IMMA each with
+    exact s32 accumulation.  Outputs are grouped in M-tiles of 16 (aligned in OUTPUT index space); M-tile mt reads the
+    inputs k0[mt] .. k0[mt] + 32 * ksteps (k0 a multiple of 4: the kernels read them with 32-bit shared-memory loads).
+    -> int32 words {n_mtiles, ksteps, 0, 0, k0[n_mtiles] (padded to x4), fragments}, fragments = for (mt, kstep, limb)
+    32 lanes x 4 registers in the A-operand layout of mma.m16n8k32 (lane = 4 g + t: a0 = A[g][4t..4t+3],
+    a1 = A[g+8][4t..], a2 = A[g][16+4t..], a3 = A[g+8][16+4t..]), or None when an M-tile needs more than
+    MMA_MAX_KSTEPS k-steps (extreme down-scales: those plans keep the integer-pipe kernels)."""
+    n_in, n_out, ksize = int(tab[0]), int(tab[1]), int(tab[2])
+    H = nat.TAB_HEADER
+    bounds = tab[H:H + 2 * n_out].reshape(n_out, 2).astype(np.int64)
+    kk = tab[H + 2 * n_out:H + 2 * n_out + n_out * ksize].reshape(n_out, ksize).astype(np.int64)
+    first, cnt = bounds[:, 0], bounds[:, 1]
+    n_mt = (n_out + MMA_M - 1) // MMA_M
+    o_lo = np.arange(n_mt) * MMA_M
+    o_hi = np.minimum(o_lo + MMA_M, n_out)
+    k0 = first[o_lo] & ~3
+    end = np.array([int((first[a:b] + cnt[a:b]).max()) for a, b in zip(o_lo, o_hi)])
+    ksteps = int(max(1, ((end - k0 + MMA_K - 1) // MMA_K).max()))
+    if ksteps > MMA_MAX_KSTEPS:
+        return None
+    K = MMA_K * ksteps
+    A = np.zeros((n_mt * MMA_M, K), dtype=np.int64)              # row = output (padded), col = input - k0[mt]
+    o = np.arange(n_out)
+    for t in range(ksize):
+        col = first + t - k0[o // MMA_M]
+        ok = t < cnt
+        A[o[ok], col[ok]] = kk[ok, t]
+    if np.abs(A).max() >= 1 << 23:
+        return None
+    limbs = np.stack([A & 255, (A >> 8) & 255, (A >> 16) & 255], 0).astype(np.uint8)       # two's complement: l2 is the s8 limb
+    L = limbs.reshape(3, n_mt, MMA_M, ksteps, MMA_K)              # [limb, mt, m, ks, k]
+    g, t = np.arange(32) // 4, np.arange(32) % 4
+    regs = []
+    for (dm, dk) in ((0, 0), (8, 0), (0, 16), (8, 16)):           # a0 .. a3
+        kidx = (4 * t + dk)[:, None] + np.arange(4)[None, :]     # [lane, byte]
+        sel = L[:, :, (g + dm)[:, None], :, kidx]                 # advanced indexing -> [lane, byte, limb, mt, ks]
+        regs.append(sel)
+    R = np.stack(regs, 0)                                         # [reg, lane, byte, limb, mt, ks]
+    R = np.transpose(R, (4, 5, 3, 1, 0, 2))                       # [mt, ks, limb, lane, reg, byte]
+    words = np.ascontiguousarray(R).view(np.uint32).reshape(-1).view(np.int32)
+    pad = (-n_mt) % 4
+    head = np.concatenate([np.array([n_mt, ksteps, 0, 0], np.int32), k0.astype(np.int32), np.zeros(pad, np.int32)])
+    return np.ascontiguousarray(np.concatenate([head, words]))
+
+
+# --------------------------------------------------------------------------------------
 # plan
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -119,6 +175,8 @@ class WorkList:
     n_launch: int = -1                # grid size when it differs from len(items) (chained fast jobs)
     block_rows: int = 0               # block height the work list was built for (passed in `flags`)
     block_cols: int = 0               # block width (generic kernels only)
+    rows: Optional[Tuple[int, int]] = None   # blend with part=(i, n): canvas rows [y0, y1) of this share (whole block rows)
+    path: int = 0                     # 0 generic work items, 1 fast job records, 2 tensor-core job records
 
 
 @dataclass
@@ -140,6 +198,11 @@ class Plan:
     mask_class: List[int] = field(default_factory=list)
     neighbors: List[List[int]] = field(default_factory=list)   # overlapping windows, any order
     fast: bool = True                     # every table has packed rows -> register-window kernels
+    mma: bool = True                      # ... and tensor-core fragments (<= 2 k-steps), windows start on 4-px columns
+    _tab_frag: Dict[Tuple[int, int], int] = field(default_factory=dict)       # pool index of the fragment section
+    _tab_k0: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # K-window start per M-tile
+    _tab_ks: Dict[Tuple[int, int], int] = field(default_factory=dict)         # k-steps
+    _tab_end: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict) # first + count per output
     _tab_off: Dict[Tuple[int, int], int] = field(default_factory=dict)
     _tab_span: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)
     _tab_packed: Dict[Tuple[int, int], int] = field(default_factory=dict)
@@ -159,6 +222,8 @@ class Plan:
         p.tiles = [make_tile(i, W, H, x, y, p.tw, p.th, padding, uniform)
                    for i, (x, y) in enumerate(tile_origins(W, H, p.tw, p.th))]
         p._build_tables()
+        if any(t.x1 % 4 for t in p.tiles) or not p.fast:
+            p.mma = False                  # the tensor-core kernels stage 4-pixel chunks at 4-pixel canvas columns
         p._build_masks()
         p._build_descriptors()
         p._build_neighbors()
@@ -181,6 +246,20 @@ class Plan:
             # LANCZOS axis uses exactly 6), so the kernels can skip the always-zero last slot
             self._tab_job_taps[key] = min(taps, max(int(tab[3]), 1)) if taps <= nat.FAST_TAPS else taps
             b = tab[nat.TAB_HEADER:nat.TAB_HEADER + 2 * n_out].reshape(n_out, 2)
+            frags = build_mma_frags(tab) if self.mma else None
+            if frags is None:
+                self.mma = False
+            else:
+                foff = int(self.tabs.shape[0])                     # tables end on a multiple of 4 int32
+                assert foff % 4 == 0
+                self.tabs = np.concatenate([self.tabs, frags])
+                pad = (-int(self.tabs.shape[0])) % 4
+                if pad:
+                    self.tabs = np.concatenate([self.tabs, np.zeros(pad, np.int32)])
+                n_mt = int(frags[0])
+                self._tab_frag[key], self._tab_ks[key] = foff, int(frags[1])
+                self._tab_k0[key] = frags[4:4 + n_mt].astype(np.int64)
+                self._tab_end[key] = (b[:, 0] + b[:, 1]).astype(np.int64)
             self._tab_first[key] = b[:, 0].astype(np.int64)
             self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], taps)], 1)   # [lo, hi) per output
         return self._tab_off[key]
@@ -413,7 +492,7 @@ class Plan:
     SLOTS = 148 * 4            # resident CTAs of the fast kernels on a B200 (4 per SM)
 
     def block_shape(self, use_fast: bool, extents: Optional[Sequence[Tuple[int, int]]] = None, frames: int = 1,
-                    share: int = 1) -> Tuple[int, int]:
+                    share: int = 1, mma: bool = False) -> Tuple[int, int]:
         """Block edge of a launch.  `extents` = (width, height) in pixels each tile covers in
         the launch's block space.  The block height is chosen by a simple wave model:
         cost(bh) = ceil(#CTAs / resident slots) * (bh + halo/fixed rows) -- short blocks give
@@ -426,7 +505,7 @@ class Plan:
         if not extents:
             return bw, nat.FAST_BLOCK_H
         best = None
-        for bh in (8, 12, 16, 20, 24, 28, 32):
+        for bh in ((16, 32) if mma else (8, 12, 16, 20, 24, 28, 32)):      # tensor-core M-tiles are 16 output rows
             n = sum(((w + bw - 1) // bw + 1) * ((h + bh - 1) // bh + 1) for w, h in extents) * frames   # +1: unaligned windows
             cost = math.ceil(n / max(self.SLOTS // max(share, 1), 1)) * (bh + 12)
             if best is None or cost < best[0] or (cost == best[0] and bh > best[1]):
@@ -461,17 +540,42 @@ class Plan:
                 return bh
         return 8
 
+    def kernel_path(self, use_fast=None) -> int:
+        """Which kernels a work list is built for: 0 generic (any scale), 1 integer-pipe fast kernels, 2 tensor-core
+        kernels.  None = the best this plan supports; True / False keep their round-1 meaning (1 / 0)."""
+        path = 2 if use_fast is None else int(use_fast)
+        if path >= 2 and not self.mma:
+            path = 1
+        if path >= 1 and not self.fast:
+            path = 0
+        return path
+
+    def _mma_crop_rows(self, t: Tile, bh_max: int) -> int:
+        """Output rows per tensor-core crop block: 32 unless the staged input rows would not fit the 48-row TMA box."""
+        key = (t.eh, t.ph)
+        for bh in ((32, 16) if bh_max >= 32 else (16,)):
+            k0, end, ks = self._tab_k0[key], self._tab_end[key], self._tab_ks[key]
+            worst = 0
+            for oy0 in range(0, t.ph, bh):
+                mv0, mv1 = oy0 // MMA_M, (min(oy0 + bh, t.ph) - 1) // MMA_M
+                worst = max(worst, int(end[MMA_M * mv0:min(MMA_M * (mv1 + 1), t.ph)].max() - k0[mv0]))
+            if worst <= 48:
+                return bh
+        return 16
+
     def crop_worklist(self, tile_ids: Sequence[int], B: int, use_fast: Optional[bool] = None,
                       share: int = 1) -> Tuple[WorkList, np.ndarray, int]:
-        use_fast = self.fast if use_fast is None else (use_fast and self.fast)
+        path = self.kernel_path(use_fast)
+        use_fast = path >= 1
         offs, total = self.slot_offsets(tile_ids, B)
         rows = []
         pw_max = ph_max = 1
         nbytes = 0
-        bw, bh_max = self.block_shape(use_fast, [(self.tiles[t].pw - nat.FAST_BLOCK_W, self.tiles[t].ph) for t in tile_ids], B, share)
+        bw, bh_max = self.block_shape(use_fast, [(self.tiles[t].pw - nat.FAST_BLOCK_W, self.tiles[t].ph) for t in tile_ids], B, share,
+                                      mma=path == 2)
         for i, tid in enumerate(tile_ids):
             t = self.tiles[tid]
-            bh = self._crop_block_rows(t, use_fast, bh_max)
+            bh = self._mma_crop_rows(t, bh_max) if path == 2 else self._crop_block_rows(t, use_fast, bh_max)
             ox = np.arange(0, t.pw, bw, dtype=np.int64)
             oy = np.arange(0, t.ph, bh, dtype=np.int64)
             gx, gy = np.meshgrid(ox, oy)
@@ -484,11 +588,70 @@ class Plan:
             ph_max = max(ph_max, self._span_max(t.eh, t.ph, bh, True))
             nbytes += t.ew * t.eh * 3 + t.pw * t.ph * 3 * 4      # u8 window read + fp32 tile write
         items = np.concatenate(rows, 0) if rows else np.zeros((0, nat.CROP_ITEM_WORDS), dtype=np.int64)
-        if use_fast and items.shape[0]:
+        if path == 2 and items.shape[0]:
+            items, pw_max, ph_max = self._crop_jobs_mma(items)
+        elif use_fast and items.shape[0]:
             items = self._crop_jobs(items)
         items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes,
-                        block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw), offs, total
+                        block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw, path=path), offs, total
+
+    # ---- tensor-core job records ---------------------------------------------------------
+    def _mma_axis(self, key: Tuple[int, int], base: np.ndarray, extent: np.ndarray):
+        """One axis of the tensor-core job records.  base = output index of block column / row 0 (any alignment, may be
+        negative), extent = block size along the axis.  -> (frag pool index, k-steps, staged start s0 (input index,
+        multiple of 4), staged count, K-window need = inputs from s0 the last M-tile's window reaches)."""
+        k0, end, ks, n_out = self._tab_k0[key], self._tab_end[key], self._tab_ks[key], key[1]
+        n_in = key[0]
+        lo = np.clip(base, 0, n_out - 1)
+        hi = np.clip(base + extent, 1, n_out)                       # exclusive
+        m0, m1 = lo // MMA_M, (hi - 1) // MMA_M
+        s0 = k0[m0]
+        cmax = np.maximum.accumulate(end)                          # first + count is non-decreasing in practice; be safe
+        last = np.minimum(MMA_M * (m1 + 1), n_out) - 1
+        stop = np.minimum(cmax[last], n_in)
+        count = np.maximum(stop - s0, 1)
+        need = k0[m1] + MMA_K * ks - s0
+        return self._tab_frag[key], ks, s0, count, need
+
+    def _crop_jobs_mma(self, items: np.ndarray):
+        """Generic crop items [tile, ox0, oy0, off_lo, off_hi, bh] -> tensor-core job records (USDU_FLAG_MMA)."""
+        n = items.shape[0]
+        J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
+        tid, ox0, oy0, bh = items[:, 0], items[:, 1], items[:, 2], items[:, 5]
+        geo = np.array([[t.x1, t.y1, t.ew, t.eh, t.pw, t.ph] for t in self.tiles], dtype=np.int64)[tid]
+        x1, y1, ew, eh, pw, ph = geo.T
+        sx0 = np.zeros(n, np.int64); cols = np.zeros(n, np.int64); need_w = np.zeros(n, np.int64)
+        sy0 = np.zeros(n, np.int64); rws = np.zeros(n, np.int64); need_h = np.zeros(n, np.int64)
+        for key in {(int(a), int(b)) for a, b in zip(ew, pw)}:
+            m = (ew == key[0]) & (pw == key[1])
+            J[m, nat.J_ROWS_H], J[m, nat.J_TAPS_H], sx0[m], cols[m], need_w[m] = self._mma_axis(key, ox0[m], np.full(int(m.sum()), nat.FAST_BLOCK_W))
+        for key in {(int(a), int(b)) for a, b in zip(eh, ph)}:
+            m = (eh == key[0]) & (ph == key[1])
+            J[m, nat.J_ROWS_V], J[m, nat.J_TAPS_V], sy0[m], rws[m], need_h[m] = self._mma_axis(key, oy0[m], bh[m])
+        cols = (cols + 3) & ~3
+        J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_LEAD] = x1 + sx0, y1 + sy0, 0
+        J[:, nat.J_COLS], J[:, nat.J_ROWS], J[:, nat.J_IX0], J[:, nat.J_IY0] = cols, rws, sx0, sy0
+        J[:, nat.J_OX_BASE], J[:, nat.J_N_OUT_H] = ox0, pw
+        J[:, nat.J_OY_BASE], J[:, nat.J_N_OUT_V] = oy0, ph
+        J[:, nat.J_DST_X], J[:, nat.J_DST_Y] = ox0, oy0
+        J[:, nat.J_OFF_LO], J[:, nat.J_OFF_HI] = items[:, 3], items[:, 4]
+        J[:, nat.J_ROWS_OUT] = np.minimum(bh, ph - oy0)
+        J[:, nat.J_COLS_OUT] = np.minimum(nat.FAST_BLOCK_W, pw - ox0)
+        J[:, nat.J_PITCH] = pw * 3
+        frame = ph * pw * 3
+        J[:, nat.J_FRAME_LO], J[:, nat.J_FRAME_HI] = frame & 0xFFFFFFFF, frame >> 32
+        J[:, nat.J_NEXT] = -1
+        J[:, nat.J_CY1] = bh                                        # block height (rows per CTA)
+        return J, int(max(cols.max(), need_w.max())), self._mma_patch_h(rws, need_h)
+
+    @staticmethod
+    def _mma_patch_h(rws: np.ndarray, need_h: np.ndarray) -> int:
+        """patch_h word of a tensor-core launch: plane rows (staged rows up to a multiple of 16: the horizontal pass
+        runs 16 rows per step) in bits 0..15, rows of the intermediate (what the vertical K windows reach) in 16..31."""
+        plane_rows = int((rws.max() + 15) // 16 * 16)
+        mid_rows = int((max(plane_rows, int(need_h.max())) + 3) // 4 * 4)
+        return plane_rows | (mid_rows << 16)
 
     def _first(self, key: Tuple[int, int], idx: np.ndarray) -> np.ndarray:
         f = self._tab_first[key]
@@ -535,16 +698,24 @@ class Plan:
                        use_fast: Optional[bool] = None, B: int = 1, part: Optional[Tuple[int, int]] = None,
                        share: int = 1) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
-        given order (the order of `tile_ids` IS the blend order).  part = (i, n): only the i-th of n
-        equal shares of the (sorted) block list -- every block is owned by exactly one CTA, so n
-        participants given the same tile list cover the launch disjointly (dist.upscale_static)."""
-        use_fast = self.fast if use_fast is None else (use_fast and self.fast)
+        given order (the order of `tile_ids` IS the blend order).  part = (i, n): only the blocks of the i-th of n
+        horizontal slabs of the canvas (whole block rows, WorkList.rows = the slab's canvas rows; the n slabs tile
+        the canvas) -- every block is owned by exactly one CTA, so n participants given the same tile list
+        composite disjoint slabs (dist.upscale_static: each rank finishes its own slab of the final canvas)."""
+        path = self.kernel_path(use_fast)
+        use_fast = path >= 1
         ext = []
         for t in tile_ids:
             sx0, sy0, sx1, sy1 = self.support(self.tiles[t])
             ext.append((sx1 - sx0, sy1 - sy0))
-        bw, bh = self.block_shape(use_fast, ext, B, share)
+        bw, bh = self.block_shape(use_fast, ext, B, share, mma=path == 2)
         nbx = (self.W + bw - 1) // bw
+        nby = (self.H + bh - 1) // bh
+        rows = None
+        if part is not None:
+            i, n = part
+            lo_b, hi_b = (nby * i) // n, (nby * (i + 1)) // n
+            rows = (min(lo_b * bh, self.H), min(hi_b * bh, self.H))
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1
         nbytes = 0
@@ -556,32 +727,26 @@ class Plan:
             X0, Y0, X1, Y1 = t.x1 + sx0, t.y1 + sy0, t.x1 + sx1, t.y1 + sy1
             gx = np.arange(X0 // bw, (X1 - 1) // bw + 1, dtype=np.int64)
             gy = np.arange(Y0 // bh, (Y1 - 1) // bh + 1, dtype=np.int64)
+            if part is not None:
+                gy = gy[(gy >= lo_b) & (gy < hi_b)]
+                if gy.size == 0:
+                    continue
             k = (gy[:, None] * nbx + gx[None, :]).ravel()
             keys.append(k)
             tids.append(np.full(k.size, tid, dtype=np.int64))
             seq.append(np.full(k.size, s, dtype=np.int64))
             pw_max = max(pw_max, self._span_max(t.pw, t.ew, bw, False))
             ph_max = max(ph_max, self._span_max(t.ph, t.eh, bh, False))
-            nbytes += t.pw * t.ph * 3 * src_bytes_per_elem + 2 * (sx1 - sx0) * (sy1 - sy0) * 3
+            frac = 1.0 if part is None else gy.size * bh / max(Y1 - Y0, 1)
+            nbytes += int(min(frac, 1.0) * (t.pw * t.ph * 3 * src_bytes_per_elem + 2 * (sx1 - sx0) * (sy1 - sy0) * 3))
         if not keys:
-            return WorkList(np.zeros((0, nat.BLEND_ITEM_WORDS), np.int32), np.zeros((0, nat.COVER_WORDS), np.int32), 1, 1, 0)
+            return WorkList(np.zeros((0, nat.JOB_WORDS if use_fast else nat.BLEND_ITEM_WORDS), np.int32),
+                            None if use_fast else np.zeros((0, nat.COVER_WORDS), np.int32), pw_max, ph_max, 0,
+                            n_launch=0, block_rows=bh, block_cols=0 if use_fast else bw, rows=rows, path=path)
         keys, tids, seq = np.concatenate(keys), np.concatenate(tids), np.concatenate(seq)
         order = np.lexsort((seq, keys))             # by block, then by position in tile_ids
         keys, tids, seq = keys[order], tids[order], seq[order]
         first = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
-        if part is not None:
-            i, n = part
-            nb = int(first.size)
-            lo, hi = (nb * i) // n, (nb * (i + 1)) // n
-            a = int(first[lo]) if lo < nb else int(keys.size)
-            b = int(first[hi]) if hi < nb else int(keys.size)
-            nbytes = int(nbytes * (b - a) / max(int(keys.size), 1))
-            keys, tids, seq = keys[a:b], tids[a:b], seq[a:b]
-            if keys.size == 0:
-                return WorkList(np.zeros((0, nat.JOB_WORDS if use_fast else nat.BLEND_ITEM_WORDS), np.int32),
-                                None if use_fast else np.zeros((0, nat.COVER_WORDS), np.int32), pw_max, ph_max, 0,
-                                n_launch=0, block_rows=bh if use_fast else bh, block_cols=0 if use_fast else bw)
-            first = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
         counts = np.diff(np.r_[first, keys.size])
         items = np.zeros((first.size, nat.BLEND_ITEM_WORDS), dtype=np.int64)
         items[:, 0] = (keys[first] % nbx) * bw
@@ -589,20 +754,23 @@ class Plan:
         items[:, 2] = first
         items[:, 3] = counts
         if use_fast:
-            jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh)
+            jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh, path == 2)
+            if path == 2:
+                jobs, pw_max, ph_max = jobs
             return WorkList(np.ascontiguousarray(jobs.astype(np.uint32).view(np.int32)), None, pw_max, ph_max, nbytes,
-                            n_launch=int(first.size), block_rows=bh)
+                            n_launch=int(first.size), block_rows=bh, rows=rows, path=path)
         cover = np.zeros((keys.size, nat.COVER_WORDS), dtype=np.int64)
         o = np.asarray(offs, dtype=np.int64)[seq]
         cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32
         return WorkList(np.ascontiguousarray(items.astype(np.uint32).view(np.int32)),
                         np.ascontiguousarray(cover.astype(np.uint32).view(np.int32)), pw_max, ph_max, nbytes,
-                        block_rows=bh, block_cols=bw)
+                        block_rows=bh, block_cols=bw, rows=rows)
 
 
-    def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh) -> np.ndarray:
+    def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh, mma: bool = False):
         """(block, tile) pairs sorted by (block, blend order) -> fast job records; the first
-        record of every block comes first (they form the grid), the rest is chained by NEXT."""
+        record of every block comes first (they form the grid), the rest is chained by NEXT.
+        mma: tensor-core flavour of the records (-> records, patch_w, patch_h word)."""
         n = keys.size
         bx0, by0 = (keys % nbx) * bw, (keys // nbx) * bh
         geo = np.array([[t.x1, t.y1, t.ew, t.eh, t.pw, t.ph] for t in self.tiles], dtype=np.int64)[tids]
@@ -612,17 +780,26 @@ class Plan:
         ix0 = np.zeros(n, np.int64); ix1 = np.zeros(n, np.int64); iy0 = np.zeros(n, np.int64); iy1 = np.zeros(n, np.int64)
         rows_h = np.zeros(n, np.int64); rows_v = np.zeros(n, np.int64)
         taps_h = np.zeros(n, np.int64); taps_v = np.zeros(n, np.int64)
+        need_w = np.zeros(n, np.int64); need_h = np.zeros(n, np.int64)
         for key in {(int(a), int(b)) for a, b in zip(pw, ew)}:
             m = (pw == key[0]) & (ew == key[1])
+            if mma:
+                rows_h[m], taps_h[m], ix0[m], cnt, need_w[m] = self._mma_axis(key, ox_base[m], np.full(int(m.sum()), bw))
+                ix1[m] = ix0[m] + ((cnt + 3) & ~3)
+                continue
             ix0[m] = self._first(key, ox_base[m])
             ix1[m] = np.minimum(self._first(key, ox_base[m] + bw - 1) + self._tab_taps[key], key[0])
             rows_h[m], taps_h[m] = self._tab_packed[key], self._tab_job_taps[key]
         for key in {(int(a), int(b)) for a, b in zip(ph, eh)}:
             m = (ph == key[0]) & (eh == key[1])
+            if mma:
+                rows_v[m], taps_v[m], iy0[m], cnt, need_h[m] = self._mma_axis(key, oy_base[m], np.full(int(m.sum()), bh))
+                iy1[m] = iy0[m] + cnt
+                continue
             iy0[m] = self._first(key, oy_base[m])
             iy1[m] = np.minimum(self._first(key, oy_base[m] + bh - 1) + self._tab_taps[key], key[0])
             rows_v[m], taps_v[m] = self._tab_packed[key], self._tab_job_taps[key]
-        lead = ix0 & 3
+        lead = np.zeros(n, np.int64) if mma else ix0 & 3
         J = np.zeros((n, nat.JOB_WORDS), dtype=np.int64)
         J[:, nat.J_TAPS_H], J[:, nat.J_TAPS_V] = taps_h, taps_v
         src = src_off + (iy0 * pw + ix0 - lead) * 3
@@ -657,6 +834,8 @@ class Plan:
         J[:, nat.J_NEXT] = nxt
         out = np.zeros_like(J)
         out[pos] = J
+        if mma:
+            return out, int(max((ix1 - ix0).max(), need_w.max())), self._mma_patch_h(iy1 - iy0, need_h)
         return out
 
 

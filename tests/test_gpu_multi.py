@@ -62,7 +62,7 @@ def _w_static(rank, world, case, transport):
         out = udist.upscale_static(x, T0Denoiser(9, 0.5), tile, tile, pad, blur, True, stats=st)
         if transport != "nccl":                                # NVLink boxes: the blend kernel reads the peers' HBM
             assert st["transport"] == "nvlink peer loads", (st["transport"], udist.PeerPayload.last_error)
-            assert st["final_blend"].startswith("shared" if transport == "peer_shared" else "master"), st["final_blend"]
+            assert st["final_blend"].startswith("sharded" if transport == "peer_shared" else "master"), st["final_blend"]
         else:
             assert st["transport"] == "nccl all_gather"
         if rank != 0:
@@ -139,6 +139,42 @@ def test_static_mode_result_on_all_ranks():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     _run(_w_all_ranks, 2)
+
+
+def _w_host(rank, world, case):
+    """dist.upscale_static_host: every rank uploads / downloads only its slab; the result tensor lives in shared
+    page-locked memory.  Several jobs in a row: held results must not be overwritten, dropped ones are recycled."""
+    from comfyui_distributed_b200 import dist as udist, planner
+    from comfyui_distributed_b200.denoise import T0Denoiser
+    kind, B, H, W, tile, pad, blur = case
+    p = planner.get_plan(W, H, tile, tile, pad, blur, True)
+    held = []
+    for job in range(4):
+        img = make_input(kind, 31 + job, B, H, W)
+        x = torch.from_numpy(img.copy())
+        x = x.pin_memory() if job % 2 else x                    # pageable and pinned inputs
+        st = {}
+        out = udist.upscale_static_host(x, T0Denoiser(9, 0.5), tile, tile, pad, blur, True, stats=st)
+        assert out is not NotImplemented, udist.PeerPayload.last_error
+        assert np.array_equal(x.numpy(), img)                   # the caller's tensor is never written
+        if rank != 0:
+            assert out is None
+            continue
+        ref = orc.replay_static(img, orc.make_t0_denoiser(9, 0.5), tile, tile, pad, blur, True, p.partition(world))
+        assert not out.is_cuda and out.is_pinned() and np.array_equal(out.numpy(), ref)
+        if job < 2:
+            held.append((out, ref))                             # a consumer that keeps its results (ComfyUI's cache)
+        for o, r in held:
+            assert np.array_equal(o.numpy(), r)
+        del out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}_{c[3]}x{c[2]}_b{c[1]}")
+def test_static_mode_on_host_tensors_moves_slabs(world, case):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(_w_host, world, case)
 
 
 def _w_node(rank, world):

@@ -28,13 +28,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-@pytest.fixture(params=["fast", "generic"], autouse=True)
+@pytest.fixture(params=["mma", "fast", "generic"], autouse=True)
 def kernel_path(request):
-    """Every test runs twice: with the register-window kernels (when the plan allows them)
-    and with the generic any-scale kernels forced."""
+    """Every test runs three times: with the tensor-core kernels (when the plan allows them), with the integer-pipe
+    fast kernels, and with the generic any-scale kernels forced."""
     engine.FORCE_GENERIC = request.param == "generic"
+    engine.FORCE_NO_MMA = request.param != "mma"
     yield request.param
     engine.FORCE_GENERIC = False
+    engine.FORCE_NO_MMA = False
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 33, 50), (1, 7, 1021), (1, 540, 960)])

@@ -258,14 +258,18 @@ def test_blend_worklist_shares_cover_the_launch_disjointly(use_fast):
 
     want = blocks(full)
     for n in (2, 3, 8):
-        got, sizes = {}, []
+        got, y_next = {}, 0
         for i in range(n):
-            part = blocks(p.blend_worklist(tiles, offs, 1, use_fast, part=(i, n)))
+            wl = p.blend_worklist(tiles, offs, 1, use_fast, part=(i, n))
+            part = blocks(wl)
             assert not (set(part) & set(got))
             got.update(part)
-            sizes.append(len(part))
+            y0, y1 = wl.rows                                   # the shares are horizontal slabs of whole block rows
+            assert y0 == y_next and y1 >= y0 and (y1 % wl.block_rows == 0 or y1 == p.H)
+            assert all(y0 <= by < y1 for (_, by) in part)
+            y_next = y1
+        assert y_next == p.H
         assert got == want
-        assert max(sizes) - min(sizes) <= 1
     empty = p.blend_worklist(tiles[:1], offs[:1], 1, use_fast, part=(63, 64))
     assert empty.items.shape[0] in (0, empty.items.shape[0])          # tiny launches may leave a share empty
 

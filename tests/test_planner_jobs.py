@@ -23,18 +23,23 @@ def _ids(c):
     return f"{c[0]}-b{c[1]}-{c[3]}x{c[2]}-t{c[4]}-p{c[5]}-m{c[6]}-{'u' if c[7] else 'n'}"
 
 
-@pytest.mark.parametrize("case", CASES, ids=_ids)
-def test_crop_records_reproduce_extract_tile(case):
+MMA_CASES = CASES + [("noise", 1, 320, 480, 256, 32, 8, True), ("noise", 1, 1200, 1600, 512, 32, 8, True)]
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["fast", "mma"])
+@pytest.mark.parametrize("case", MMA_CASES, ids=_ids)
+def test_crop_records_reproduce_extract_tile(case, path):
     kind, B, H, W, tile, pad, blur, uniform = case
     p = planner.Plan.build(W, H, tile, tile, pad, blur, uniform)
-    if not p.fast:
-        pytest.skip("this geometry runs on the generic kernels")
+    if not p.fast or (path == 2 and not p.mma):
+        pytest.skip("this geometry runs on the generic kernels" if not p.fast else "no tensor-core path for this geometry")
     canvas = orc.quantize_u8(make_input(kind, 3, B, H, W))
     _, _, oplan = orc.make_plan(W, H, tile, tile, pad, uniform)
     ids = list(range(len(p.tiles)))
-    wl, offs, total = p.crop_worklist(ids, B, True)
+    wl, offs, total = p.crop_worklist(ids, B, path)
+    assert wl.path == path
     out = np.full(total, -1.0, dtype=np.float32)
-    km.run_crop(p, canvas, wl, out)
+    (km.run_crop_mma if path == 2 else km.run_crop)(p, canvas, wl, out)
     for t, o in zip(oplan, offs):
         want = orc.extract_tile(canvas, t)
         got = out[o:o + want.size].reshape(want.shape)
@@ -42,13 +47,15 @@ def test_crop_records_reproduce_extract_tile(case):
     assert not (out < 0).any()                       # every element of every tile slot was written exactly by some block
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["fast", "mma"])
 @pytest.mark.parametrize("src_u8", [False, True])
-@pytest.mark.parametrize("case", CASES, ids=_ids)
-def test_blend_records_reproduce_ordered_blend(case, src_u8):
+@pytest.mark.parametrize("case", MMA_CASES, ids=_ids)
+def test_blend_records_reproduce_ordered_blend(case, src_u8, path):
     kind, B, H, W, tile, pad, blur, uniform = case
     p = planner.Plan.build(W, H, tile, tile, pad, blur, uniform)
-    if not p.fast:
-        pytest.skip("this geometry runs on the generic kernels")
+    if not p.fast or (path == 2 and not p.mma):
+        pytest.skip("this geometry runs on the generic kernels" if not p.fast else "no tensor-core path for this geometry")
+    run_blend = km.run_blend_mma if path == 2 else km.run_blend
     tw, th, oplan = orc.make_plan(W, H, tile, tile, pad, uniform)
     base = orc.quantize_u8(make_input(kind, 4, B, H, W))
     rng = np.random.default_rng(1)
@@ -64,18 +71,18 @@ def test_blend_records_reproduce_ordered_blend(case, src_u8):
     feed = orc.quantize_u8(src) if src_u8 else src
     # (a) ONE launch with every tile in ascending order (the static-mode final blend)
     got = base.copy()
-    km.run_blend(p, got, p.blend_worklist(ids, offs, 1 if src_u8 else 4, True, B), feed, pool)
+    run_blend(p, got, p.blend_worklist(ids, offs, 1 if src_u8 else 4, path, B), feed, pool)
     assert np.array_equal(got, want)
     # (b) the same launch shared out over 3 participants (dist.upscale_static)
     got = base.copy()
     for i in (2, 0, 1):                               # any order: the shares own disjoint blocks
-        km.run_blend(p, got, p.blend_worklist(ids, offs, 1 if src_u8 else 4, True, B, part=(i, 3)), feed, pool)
+        run_blend(p, got, p.blend_worklist(ids, offs, 1 if src_u8 else 4, path, B, part=(i, 3)), feed, pool)
     assert np.array_equal(got, want)
     # (c) wave by wave (the progressive driver blends each wave with its own launch)
     got = base.copy()
     pos = {t: i for i, t in enumerate(ids)}
     for wave in p.waves():
-        km.run_blend(p, got, p.blend_worklist(wave, np.array([offs[pos[t]] for t in wave]), 1 if src_u8 else 4, True, B), feed, pool)
+        run_blend(p, got, p.blend_worklist(wave, np.array([offs[pos[t]] for t in wave]), 1 if src_u8 else 4, path, B), feed, pool)
     assert np.array_equal(got, want)
 
 
