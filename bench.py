@@ -110,11 +110,102 @@ def result_digest(out) -> str:
 
 
 # --------------------------------------------------------------------------------------
-# CPU baseline (oracle/ref_port.py: the reference's Pillow path, same cost structure)
+# CPU baseline: the reference's OWN code (oracle/make_ref.py bundles its sources into the git-ignored oracle/_ref/
+# at build time; oracle/ref_loader.py loads them under ComfyUI stand-ins), on a bounded sample of the workload
 # --------------------------------------------------------------------------------------
-def cpu_port_sample(workload: str, budget_s: float):
+def _oracle_path():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _t0_torch():
+    """The T0 sampler stand-in on torch CPU tensors (same arithmetic as denoise.T0Denoiser / oracle.make_t0_denoiser)."""
+    import numpy as np
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cache = {}
+
+    def fn(pixels, seed, denoise):
+        key = (tuple(pixels.shape), int(seed))
+        if key not in cache:
+            cache[key] = torch.rand(tuple(pixels.shape), generator=torch.Generator().manual_seed(int(seed)), dtype=torch.float32)
+        d = np.float32(denoise)
+        return torch.clamp(pixels * float(np.float32(1.0) - d) + cache[key] * float(d), 0.0, 1.0)
+
+    return fn
+
+
+def reference_available() -> bool:
+    _oracle_path()
+    import make_ref
+    return bool(make_ref.staged_root())
+
+
+def real_reference_sample(workload: str, n_tiles: int):
+    """N = 1: the reference's process_single_gpu (upscale/modes/single_gpu.py:8-72), unmodified, on the FIRST n_tiles tiles
+    of the full canvas (its calculate_tiles is wrapped on the node object; every per-tile cost -- full-canvas mask, full-canvas
+    tensor<->PIL conversions, full-canvas RGBA composite -- is the real one).  Job time = fixed part (a 0-tile run: the
+    conversions around the loop) + per-tile time x all tiles."""
+    import torch
+    _oracle_path()
+    import ref_loader
+    B, H, W, tile, pad, blur = WORKLOADS[workload]
+    img = make_canvas_cpu(B, H, W)
+    node, fake_nodes = ref_loader.make_reference_node()
+    fake_nodes.fn = _t0_torch()
+    full = node.calculate_tiles
+    total = len(full(W, H, node.round_to_multiple(tile), node.round_to_multiple(tile), True))
+    cond = [[torch.zeros(1, 77, 8), {}]]
+
+    def run(k):
+        node.calculate_tiles = lambda *a, **kw: full(*a, **kw)[:k]
+        t0 = time.perf_counter()
+        node.process_single_gpu(img, None, cond, cond, None, SEED, 20, 8.0, "euler", "normal", DENOISE, tile, tile, pad, blur, True, False)
+        return time.perf_counter() - t0
+
+    fixed = run(0)
+    n_tiles = max(1, min(n_tiles, total))
+    wall = run(n_tiles)
+    per_tile = max(wall - fixed, 1e-9) / n_tiles
+    est = fixed + per_tile * total
+    mp = B * H * W / 1e6
+    return {"value": mp / est, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"the reference's own process_single_gpu on the first {n_tiles} of {total} tiles of {workload} (full canvas, T0 sampler): "
+                      f"fixed {fixed:.1f}s + {per_tile:.2f}s/tile -> {est:.0f}s/job extrapolated; Pillow is single-threaded, torch ops use `cores` threads",
+            "host_cpus": os.cpu_count(), "source": f"oracle/_ref (oracle/make_ref.py) via oracle/ref_loader.py: {ref_loader.REF_ROOT}"}
+
+
+def real_reference_static_sample(workload: str, participants: int, tiles_per_participant: int):
+    """N > 1: the reference's static mode really run -- master + N-1 workers, its own HTTP routes on an aiohttp server on
+    127.0.0.1, its PNG-multipart transport, its pull queue and its sorted final blend (upscale/modes/static.py:191-570,
+    upscale/worker_comms.py:16-188) -- on a job of the first N x tiles_per_participant tiles of the full canvas.  Every phase
+    of that mode is linear in the number of tiles, so job time = fixed + (sample - fixed) x all tiles / sample tiles."""
+    import torch
+    _oracle_path()
+    import ref_static_run
+    import usdu_oracle as orc
+    B, H, W, tile, pad, blur = WORKLOADS[workload]
+    img = make_canvas_cpu(B, H, W).numpy()
+    total = len(orc.make_plan(W, H, tile, tile, pad, True)[2])
+    k = max(1, min(participants * tiles_per_participant, total))
+    t0 = time.perf_counter()
+    _, asg = ref_static_run.run_static(img, participants - 1, tile, pad, blur, True, SEED, DENOISE, job_id=f"bench{time.time_ns()}",
+                                       timeout=1500.0, max_tiles=k)
+    wall = time.perf_counter() - t0
+    fixed = min(0.25 * wall, 2.0 * B * H * W * 3 * 4 / 1e9)          # tensor<->PIL conversions around the loop (~2 s per GB)
+    est = fixed + (wall - fixed) * total / k
+    mp = B * H * W / 1e6
+    return {"value": mp / est, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "reference", "participants": participants,
+            "sample": f"the reference's own static mode (master + {participants - 1} workers as threads of one process -- Pillow and torch "
+                      f"release the GIL in their C loops --, real aiohttp routes + PNG transport on 127.0.0.1) on the first {k} of {total} "
+                      f"tiles of {workload}: {wall:.1f}s, tiles per participant {[len(a) for a in asg]} -> {est:.0f}s/job extrapolated linearly",
+            "host_cpus": os.cpu_count(), "source": f"oracle/_ref via oracle/ref_static_run.py: {ref_static_run.REF_ROOT}"}
+
+
+def cpu_port_sample(workload: str, budget_s: float):
+    """Fallback when the reference bundle is absent: oracle/ref_port.py, the port with the reference's cost structure."""
+    import torch
+    _oracle_path()
     import ref_port
     B, H, W, tile, pad, blur = WORKLOADS[workload]
     img = make_canvas_cpu(B, H, W)
@@ -134,36 +225,37 @@ def cpu_port_sample(workload: str, budget_s: float):
             "host_cpus": os.cpu_count(), "phases_s": {k: round(v, 3) for k, v in t.items() if isinstance(v, float)}}
 
 
+def cpu_baseline_sample(workload: str, n_tiles: int, budget_s: float):
+    return real_reference_sample(workload, n_tiles) if reference_available() else cpu_port_sample(workload, budget_s)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.
-    N == 1: single-process progressive path.  N > 1: the N-participant HTTP + PNG static
-    mode (oracle/ref_port_http.py), master + N-1 local worker processes."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, one bounded sample
+    (whatever --steps says: a sample is tens of seconds to minutes of CPU work).  N == 1: process_single_gpu.
+    N > 1: the N-participant HTTP + PNG static mode.  Falls back to the cost-faithful port (oracle/ref_port*.py) only
+    when oracle/_ref is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workload = args.workload
     B, H, W, tile, pad, blur = WORKLOADS[workload]
     mp = B * H * W / 1e6
-    vals = []
-    detail = None
     steps = max(1, args.steps)
-    # every step is a bounded sample; the whole run stays within ~2.5 minutes whatever K is
-    budget = max(3.0, min(args.ref_budget, 150.0 / steps))
-    t_start = time.perf_counter()
-    for _ in range(steps):
-        if vals and time.perf_counter() - t_start > 150.0:
-            break                                         # (N > 1: a sample is a whole HTTP job of a few tiles)
+    if reference_available():
         if args.gpus == 1:
-            detail = cpu_port_sample(workload, budget)
+            detail = real_reference_sample(workload, args.ref_tiles)
         else:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import ref_port_http
-            detail = ref_port_http.bench_sample(WORKLOADS[workload], SEED, DENOISE, participants=args.gpus,
-                                                tiles_per_participant=args.ref_tiles_per_participant)
-        vals.append(detail["value"])
-    v = sum(vals) / len(vals)
+            detail = real_reference_static_sample(workload, args.gpus, args.ref_tiles_per_participant)
+    elif args.gpus == 1:
+        detail = cpu_port_sample(workload, min(args.ref_budget, 60.0))
+    else:
+        _oracle_path()
+        import ref_port_http
+        detail = ref_port_http.bench_sample(WORKLOADS[workload], SEED, DENOISE, participants=args.gpus,
+                                            tiles_per_participant=args.ref_tiles_per_participant)
+    v = detail["value"]
     line = {"impl": "reference", "metric": "megapixels/sec", "value": v, "unit": "MP/s", "n_gpus": args.gpus,
-            "steps": len(vals), "requested_steps": steps, "warmup": 0, "ms_per_step": mp / v * 1e3, "higher_is_better": True,
+            "steps": 1, "requested_steps": steps, "warmup": 0, "ms_per_step": mp / v * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "canvas": [B, H, W], "tile": tile, "padding": pad, "mask_blur": blur,
                        "denoiser": "T0 deterministic stand-in", "timing": "wall clock, extrapolated from a bounded sample"},
@@ -186,7 +278,9 @@ def main():
     ap.add_argument("--denoiser", default="t0", choices=["t0", "t1"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=20.0)
-    ap.add_argument("--ref-tiles-per-participant", type=int, default=1)
+    ap.add_argument("--ref-tiles-per-participant", type=int, default=3)
+    ap.add_argument("--ref-tiles", type=int, default=6, help="tiles of the bounded sample of --impl reference at N = 1")
+    ap.add_argument("--cpu-tiles", type=int, default=3, help="tiles of the bounded cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-t1", action="store_true", help="skip the supplementary SDXL-cost (T1) measurement")
     args = ap.parse_args()
@@ -446,7 +540,7 @@ def main():
     if t1_info is not None:
         line["sdxl_cost_tier"] = t1_info
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_port_sample(args.workload, args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline_sample(args.workload, args.cpu_tiles, args.cpu_budget)
     print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()

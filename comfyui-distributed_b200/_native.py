@@ -26,6 +26,7 @@ TAB_HEADER = 8
 PACKED_ROW = 8
 FLAG_FAST = 1
 FLAG_MMA = 2
+FLAG_MMA_KS2 = 4
 FLAG_REMOTE_CANVAS = 1 << 24
 FILTER_LANCZOS, FILTER_BICUBIC = 0, 1
 CROP_ITEM_WORDS = 6

@@ -450,10 +450,10 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
 
 namespace usdu { namespace mma {
 int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
-                int patch_w, int patch_h, float* out, cudaStream_t st);
+                int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st);
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
                  const int32_t* items, int n_items, int patch_w, int patch_h, const void* src, int src_is_u8, int block_rows,
-                 cudaStream_t st);
+                 int two_ksteps, cudaStream_t st);
 } }
 
 using namespace usdu;
@@ -627,7 +627,8 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
     USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_crop_resize: pitch must be >= 3*W and a multiple of 16");
     if (flags & USDU_FLAG_MMA) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: tensor-core path needs tables");
-        return mma::launch_crop(canvas_dev, B, H, W, pitch, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev, (cudaStream_t)stream);
+        return mma::launch_crop(canvas_dev, B, H, W, pitch, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev,
+                                (flags & USDU_FLAG_MMA_KS2) ? 1 : 0, (cudaStream_t)stream);
     }
     if (flags & USDU_FLAG_FAST) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: fast path needs tables");
@@ -662,7 +663,7 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, con
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: tensor-core path needs tables");
         USDU_REQUIRE(((uintptr_t)src_dev & 15) == 0, "usdu_tile_blend: src must be 16-byte aligned");
         return mma::launch_blend(canvas_dev, B, H, W, pitch, tabs_dev, mask_pool_dev, items_dev, n_items, patch_w, patch_h, src_dev,
-                                 src_is_u8, (flags >> 8) & 0xFF, (cudaStream_t)stream);
+                                 src_is_u8, (flags >> 8) & 0xFF, (flags & USDU_FLAG_MMA_KS2) ? 1 : 0, (cudaStream_t)stream);
     }
     if (flags & USDU_FLAG_FAST) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_blend: fast path needs tables");

@@ -26,6 +26,11 @@ namespace usdu {
 namespace mma {
 
 constexpr int kT = 256;                     // 8 warps
+#ifndef USDU_MMA_CTAS
+#define USDU_MMA_CTAS 3                      // resident CTAs per SM the kernels are compiled for: 80 registers, no spills; 4 (64 registers,
+                                             // 92 B of spills in the feather V pass) is faster for the crop alone at full launches (244 vs 260 us
+                                             // for all 135 tiles of cfg2) but slower inside the 31-wave job (profiles/r02f_kernel_bench_*.txt)
+#endif
 constexpr int BWX = USDU_FAST_BLOCK_W;      // 128-pixel wide blocks
 constexpr int MIDP = 440;                   // words per row group of the intermediate: >= 3 * 144 columns, == 24 mod 32
 constexpr int kDBox = BWX * 3 / 2;          // canvas block = two bulk-tensor boxes of 192 bytes per row
@@ -57,10 +62,15 @@ __device__ __forceinline__ void mma_su(int (&d)[4], const uint32_t (&a)[4], uint
         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Pillow's clip8((acc) >> 22) of the recombined limbs (limb 0 starts at the rounding constant 2^21)
-__device__ __forceinline__ uint32_t finish(int l0, int l1, int l2) {
-    const int acc = l0 + (l1 << 8) + (l2 << 16);
-    return (uint32_t)__vimin_s32_relu(acc >> kPrecisionBits, 255);
+// Pillow's accumulator >> 22 of the recombined limbs (limb 0 starts at the rounding constant 2^21); clip8 happens in pack2
+__device__ __forceinline__ int combine(int l0, int l1, int l2) {
+    return (l0 + (l1 << 8) + (l2 << 16)) >> kPrecisionBits;
+}
+// (upper << 16) | clip8(hi) << 8 | clip8(lo): one I2IP (cvt.pack.sat) instead of two clamps, a shift and an OR
+__device__ __forceinline__ uint32_t pack2(int lo, int hi, uint32_t upper) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+    return d;
 }
 
 // fragment section of a table (planner.build_mma_frags)
@@ -88,22 +98,20 @@ struct FragTable {
 // n.  Lane t holds n = 2t, 2t+1 of both tiles; lanes t and t^1 swap so that even t gets n = 4(t/2)..+3 (tile A) and
 // odd t gets n = 8 + 4(t/2)..+3 (tile B).  Returns the 4-group index within the 16 (0..3).
 __device__ __forceinline__ int pack16(const int (&dA)[3][4], const int (&dB)[3][4], int t, uint32_t (&word)[2]) {
-    uint32_t pA[2], pB[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        pA[h] = finish(dA[0][2 * h], dA[1][2 * h], dA[2][2 * h]) | (finish(dA[0][2 * h + 1], dA[1][2 * h + 1], dA[2][2 * h + 1]) << 8);
-        pB[h] = finish(dB[0][2 * h], dB[1][2 * h], dB[2][2 * h]) | (finish(dB[0][2 * h + 1], dB[1][2 * h + 1], dB[2][2 * h + 1]) << 8);
-    }
     const bool odd = t & 1;
-    const uint32_t send = odd ? (pA[0] | (pA[1] << 16)) : (pB[0] | (pB[1] << 16));
-    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    if (!odd) {
-        word[0] = pA[0] | (recv << 16);
-        word[1] = pA[1] | (recv & 0xffff0000u);
-    } else {
-        word[0] = (recv & 0xffffu) | (pB[0] << 16);
-        word[1] = (recv >> 16) | (pB[1] << 16);
+    int keep[4], give[4];                       // [2 h + i]: the tile this lane keeps (A if even, B if odd) and the one it hands over
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int va = combine(dA[0][i], dA[1][i], dA[2][i]), vb = combine(dB[0][i], dB[1][i], dB[2][i]);
+        keep[i] = odd ? vb : va;
+        give[i] = odd ? va : vb;
     }
+    const uint32_t send = pack2(give[0], give[1], pack2(give[2], give[3], 0));      // h = 0 pair low, h = 1 pair high
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    // even lanes: own pair = n 4j, 4j+1 (low half), partner's = 4j+2, 4j+3 (high half); odd lanes the other way round
+    const uint32_t k0 = pack2(keep[0], keep[1], 0), k1 = pack2(keep[2], keep[3], 0);
+    word[0] = odd ? __byte_perm(recv, k0, 0x5410) : __byte_perm(k0, recv, 0x5410);
+    word[1] = odd ? __byte_perm(recv, k1, 0x5432) : __byte_perm(k1, recv, 0x7610);
     return (t >> 1) + (odd ? 2 : 0);
 }
 
@@ -222,30 +230,55 @@ __device__ __forceinline__ void deinterleave(uint32_t w0, uint32_t w1, uint32_t 
 }
 
 // fp32 source in [0,1] (sampler output): Q1 truncation on the fly.  src -> first float of the staged patch.
+// kU units per thread per trip, every load issued before the first use (12 x 16 bytes in flight per thread).
 __device__ __forceinline__ void stage_f32(uint8_t* planes, int PB, int plane_rows, const float* __restrict__ src, int64_t pitch_f,
                                           int rows, int cols) {
-    const int chunks = cols >> 2;
-    for (int i = threadIdx.x; i < rows * chunks; i += kT) {
-        const int r = i / chunks, ch = i - r * chunks;
-        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch_f) + ch * 3;
-        const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2);
-        const uint32_t R = quant_u8(f0.x) | (quant_u8(f0.w) << 8) | (quant_u8(f1.z) << 16) | (quant_u8(f2.y) << 24);
-        const uint32_t G = quant_u8(f0.y) | (quant_u8(f1.x) << 8) | (quant_u8(f1.w) << 16) | (quant_u8(f2.z) << 24);
-        const uint32_t B = quant_u8(f0.z) | (quant_u8(f1.y) << 8) | (quant_u8(f2.x) << 16) | (quant_u8(f2.w) << 24);
-        store_planes(planes, PB, plane_rows, r, ch, R, G, B);
+    constexpr int kU = 3;
+    const int chunks = cols >> 2, total = rows * chunks;
+    for (int i0 = threadIdx.x; i0 < total; i0 += kT * kU) {
+        float4 f[kU][3];
+        int rr[kU], cc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int i = min(i0 + u * kT, total - 1);
+            rr[u] = i / chunks; cc[u] = i - rr[u] * chunks;
+            const float4* p = reinterpret_cast<const float4*>(src + (int64_t)rr[u] * pitch_f) + cc[u] * 3;
+            f[u][0] = __ldg(p); f[u][1] = __ldg(p + 1); f[u][2] = __ldg(p + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (i0 + u * kT >= total) break;
+            const float4 f0 = f[u][0], f1 = f[u][1], f2 = f[u][2];
+            const uint32_t R = quant_u8(f0.x) | (quant_u8(f0.w) << 8) | (quant_u8(f1.z) << 16) | (quant_u8(f2.y) << 24);
+            const uint32_t G = quant_u8(f0.y) | (quant_u8(f1.x) << 8) | (quant_u8(f1.w) << 16) | (quant_u8(f2.z) << 24);
+            const uint32_t B = quant_u8(f0.z) | (quant_u8(f1.y) << 8) | (quant_u8(f2.x) << 16) | (quant_u8(f2.w) << 24);
+            store_planes(planes, PB, plane_rows, rr[u], cc[u], R, G, B);
+        }
     }
 }
 
 // u8 interleaved source in global memory (transport payload, canvas without TMA); src 4-byte aligned
 __device__ __forceinline__ void stage_u8(uint8_t* planes, int PB, int plane_rows, const uint8_t* __restrict__ src, int64_t pitch,
                                          int rows, int cols) {
-    const int chunks = cols >> 2;
-    for (int i = threadIdx.x; i < rows * chunks; i += kT) {
-        const int r = i / chunks, ch = i - r * chunks;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (int64_t)r * pitch) + ch * 3;
-        uint32_t R, G, B;
-        deinterleave(__ldg(p), __ldg(p + 1), __ldg(p + 2), R, G, B);
-        store_planes(planes, PB, plane_rows, r, ch, R, G, B);
+    constexpr int kU = 4;
+    const int chunks = cols >> 2, total = rows * chunks;
+    for (int i0 = threadIdx.x; i0 < total; i0 += kT * kU) {
+        uint32_t w[kU][3];
+        int rr[kU], cc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int i = min(i0 + u * kT, total - 1);
+            rr[u] = i / chunks; cc[u] = i - rr[u] * chunks;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (int64_t)rr[u] * pitch) + cc[u] * 3;
+            w[u][0] = __ldg(p); w[u][1] = __ldg(p + 1); w[u][2] = __ldg(p + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (i0 + u * kT >= total) break;
+            uint32_t R, G, B;
+            deinterleave(w[u][0], w[u][1], w[u][2], R, G, B);
+            store_planes(planes, PB, plane_rows, rr[u], cc[u], R, G, B);
+        }
     }
 }
 
@@ -266,15 +299,16 @@ __device__ __forceinline__ void stage_raw(uint8_t* planes, int PB, int plane_row
     }
 }
 
-template <class Epilogue>
+// KSMAX = 1: every axis of the launch fits one k-step (scales up to ~1.4): no two-step code, fewer registers
+template <int KSMAX, class Epilogue>
 __device__ __forceinline__ void both_passes(const uint8_t* planes, uint32_t* mid, const int32_t* tabs, const JobView& J, int PB,
                                             int plane_rows, int bh, Epilogue& epi) {
     const int steps16 = (J[USDU_J_ROWS] + 15) >> 4;
-    if (J[USDU_J_TAPS_H] <= 1) hpass<1>(planes, mid, tabs, J, PB, plane_rows, steps16);
-    else hpass<2>(planes, mid, tabs, J, PB, plane_rows, steps16);
+    if (KSMAX == 1 || J[USDU_J_TAPS_H] <= 1) hpass<1>(planes, mid, tabs, J, PB, plane_rows, steps16);
+    else hpass<KSMAX>(planes, mid, tabs, J, PB, plane_rows, steps16);
     __syncthreads();
-    if (J[USDU_J_TAPS_V] <= 1) vpass<1>(mid, tabs, J, bh, epi);
-    else vpass<2>(mid, tabs, J, bh, epi);
+    if (KSMAX == 1 || J[USDU_J_TAPS_V] <= 1) vpass<1>(mid, tabs, J, bh, epi);
+    else vpass<KSMAX>(mid, tabs, J, bh, epi);
 }
 
 // ======================================================================================
@@ -296,8 +330,8 @@ struct CropEpilogue {
     }
 };
 
-template <bool kTma>
-__global__ void __launch_bounds__(kT, 3)
+template <bool kTma, int KSMAX>
+__global__ void __launch_bounds__(kT, KSMAX == 1 ? USDU_MMA_CTAS : 3)
 crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int plane_rows, int mid_rows, int W3,
                 const __grid_constant__ CUtensorMap cmap) {
@@ -342,7 +376,7 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
     epi.ow3 = J[USDU_J_COLS_OUT] * 3;
     epi.rows_out = J[USDU_J_ROWS_OUT];
     epi.lut = lut;
-    both_passes(planes, mid, tabs, J, PB, plane_rows, J[USDU_J_CY1], epi);
+    both_passes<KSMAX>(planes, mid, tabs, J, PB, plane_rows, J[USDU_J_CY1], epi);
 }
 
 // ======================================================================================
@@ -411,8 +445,8 @@ struct BlendFeather {
     }
 };
 
-template <bool kSrcU8>
-__global__ void __launch_bounds__(kT, 3)
+template <bool kSrcU8, int KSMAX>
+__global__ void __launch_bounds__(kT, KSMAX == 1 ? USDU_MMA_CTAS : 3)
 blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool, const int32_t* __restrict__ jobs,
                  const void* __restrict__ src_v, int W3, int patch_w, int plane_rows, int mid_rows, int block_rows,
                  const __grid_constant__ CUtensorMap cmap) {
@@ -458,7 +492,7 @@ blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ m
             BlendOpaque epi;
             epi.d = D;
             epi.rows = J[USDU_J_ROWS_OUT];
-            both_passes(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
+            both_passes<KSMAX>(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
         } else {
             BlendFeather epi;
             epi.d = D;
@@ -466,7 +500,7 @@ blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ m
             epi.mask = mask_pool + J.i64(USDU_J_OFF_LO);
             epi.cx0 = J[USDU_J_CX0]; epi.cx1 = J[USDU_J_CX1];
             epi.cy0 = J[USDU_J_CY0]; epi.cy1 = J[USDU_J_CY1];
-            both_passes(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
+            both_passes<KSMAX>(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
         }
         idx = J[USDU_J_NEXT];
         first = false;
@@ -509,8 +543,17 @@ static int split_patch_h(int patch_h, int* plane_rows, int* mid_rows, const char
     return USDU_OK;
 }
 
+template <class K, class... Args>
+static int launch_one(K kernel, size_t smem, dim3 grid, cudaStream_t st, Args... args) {
+    int s = optin((const void*)kernel, smem);
+    if (s != USDU_OK) return s;
+    USDU_CUDA(launch_pdl(kernel, grid, dim3(kT), smem, st, args...));
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
 int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
-                int patch_w, int patch_h, float* out, cudaStream_t st) {
+                int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st) {
     int plane_rows, mid_rows;
     int s = split_patch_h(patch_h, &plane_rows, &mid_rows, "usdu_tile_crop_resize");
     if (s != USDU_OK) return s;
@@ -520,20 +563,18 @@ int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const
     bool use_tma = plane_rows <= kBoxR && 12 + patch_w * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
     if (use_tma) use_tma = tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kBoxB, kBoxR);
     const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, use_tma);
-    const void* fn = use_tma ? (const void*)crop_mma_kernel<true> : (const void*)crop_mma_kernel<false>;
-    s = optin(fn, smem);
-    if (s != USDU_OK) return s;
+    const dim3 grid(n_items, B);
+    const int W3 = W * 3;
     if (use_tma)
-        USDU_CUDA(launch_pdl(crop_mma_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W * 3, cmap));
-    else
-        USDU_CUDA(launch_pdl(crop_mma_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W * 3, cmap));
-    USDU_CUDA(cudaGetLastError());
-    return USDU_OK;
+        return two_ksteps ? launch_one(crop_mma_kernel<true, 2>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
+                          : launch_one(crop_mma_kernel<true, 1>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+    return two_ksteps ? launch_one(crop_mma_kernel<false, 2>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
+                      : launch_one(crop_mma_kernel<false, 1>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
 }
 
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
                  const int32_t* items, int n_items, int patch_w, int patch_h, const void* src, int src_is_u8, int block_rows,
-                 cudaStream_t st) {
+                 int two_ksteps, cudaStream_t st) {
     if (block_rows != 16 && block_rows != 32) {
         set_error("usdu_tile_blend: the tensor-core path needs a block height of 16 or 32 in flags bits 8..15, got %d", block_rows);
         return USDU_ERR_INVALID;
@@ -549,15 +590,13 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
         return USDU_ERR_CUDA;
     }
     const size_t smem = blend_smem(patch_w, plane_rows, mid_rows, block_rows);
-    const void* fn = src_is_u8 ? (const void*)blend_mma_kernel<true> : (const void*)blend_mma_kernel<false>;
-    s = optin(fn, smem);
-    if (s != USDU_OK) return s;
+    const dim3 grid(n_items, B);
+    const int W3 = W * 3;
     if (src_is_u8)
-        USDU_CUDA(launch_pdl(blend_mma_kernel<true>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, plane_rows, mid_rows, block_rows, cmap));
-    else
-        USDU_CUDA(launch_pdl(blend_mma_kernel<false>, dim3(n_items, B), dim3(kT), smem, st, tabs, mask_pool, items, src, W * 3, patch_w, plane_rows, mid_rows, block_rows, cmap));
-    USDU_CUDA(cudaGetLastError());
-    return USDU_OK;
+        return two_ksteps ? launch_one(blend_mma_kernel<true, 2>, smem, grid, st, tabs, mask_pool, items, src, W3, patch_w, plane_rows, mid_rows, block_rows, cmap)
+                          : launch_one(blend_mma_kernel<true, 1>, smem, grid, st, tabs, mask_pool, items, src, W3, patch_w, plane_rows, mid_rows, block_rows, cmap);
+    return two_ksteps ? launch_one(blend_mma_kernel<false, 2>, smem, grid, st, tabs, mask_pool, items, src, W3, patch_w, plane_rows, mid_rows, block_rows, cmap)
+                      : launch_one(blend_mma_kernel<false, 1>, smem, grid, st, tabs, mask_pool, items, src, W3, patch_w, plane_rows, mid_rows, block_rows, cmap);
 }
 
 }  // namespace mma

@@ -219,7 +219,7 @@ class StaticJob:
         if self.sharded:
             self.final_canvas = Canvas(self.dp, B, self.final.buf[: self.canvas_bytes].view(B, plan.H, pitch))
             offs = peer_offsets(self.final_order, self.where, self.peer.ptrs, self.rank)
-            wl = self.dp.blend_list(tuple(self.final_order), offs, True, self.final_canvas.path, B, (self.rank, world))[0]
+            wl = self.dp.blend_list(tuple(self.final_order), offs, True, self.final_canvas.path_blend, B, (self.rank, world))[0]
             self.final_offs = offs
             bh = max(wl.block_rows, 1)
             nby = (plan.H + bh - 1) // bh

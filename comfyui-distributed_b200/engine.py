@@ -70,6 +70,10 @@ class KernelProfile:
 PROFILE: Optional[KernelProfile] = None
 FORCE_GENERIC = False     # tests: run the generic (any-scale) kernels even when the fast ones apply
 FORCE_NO_MMA = os.environ.get("USDU_NO_MMA", "0") == "1"   # tests / A-B runs: integer-pipe fast kernels instead of the tensor-core ones
+PATH_FLAGS = (0, nat.FLAG_FAST, nat.FLAG_MMA)
+_PATHS = {"generic": 0, "fast": 1, "mma": 2}
+PATH_CROP = _PATHS[os.environ.get("USDU_CROP_PATH", "mma")]      # best build per kernel (upper bound: the plan may not support it)
+PATH_BLEND = _PATHS[os.environ.get("USDU_BLEND_PATH", "mma")]
 USE_CUDA_GRAPHS = True    # capture the wave loop when the sampler is cuda_graph_safe
 
 
@@ -144,7 +148,10 @@ class Canvas:
         self.launches = 0
         self.algo_bytes = 0
         self.path = 0 if FORCE_GENERIC else self.plan.kernel_path(1 if FORCE_NO_MMA else None)   # 0 generic, 1 fast, 2 tensor-core
-        self.flags = (0, nat.FLAG_FAST, nat.FLAG_MMA)[self.path]
+        # per kernel: the tensor-core build where it is the faster one on B200 (profiles/r02*_kernel_bench*), the
+        # integer-pipe build otherwise; both give identical bytes
+        self.path_crop = min(self.path, PATH_CROP)
+        self.path_blend = min(self.path, PATH_BLEND)
         self.share = 1                      # launches expected to run side by side (tile-granular schedule)
 
     @staticmethod
@@ -186,7 +193,7 @@ class Canvas:
         """-> (flat fp32 buffer, element offsets per tile).  Tile i is
         buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
         tile_ids = tuple(int(t) for t in tile_ids)
-        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, self.path, self.share)
+        wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, self.path_crop, self.share)
         if out is None:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
@@ -196,7 +203,8 @@ class Canvas:
                 lambda: nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch,
                                              self.dp.tiles.data_ptr(), self.dp.tabs.data_ptr(), items.data_ptr(),
                                              items.shape[0], wl.patch_w, wl.patch_h, out.data_ptr(),
-                                             self.flags | (wl.block_rows << 8) | (wl.block_cols << 16), _stream_ptr()))
+                                             PATH_FLAGS[wl.path] | (wl.block_rows << 8) | (wl.block_cols << 16) |
+                                             (nat.FLAG_MMA_KS2 if wl.ks2 else 0), _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
         return out, offs
@@ -213,14 +221,14 @@ class Canvas:
         if src.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"blend: src must be float32 or uint8, got {src.dtype}")
         src_u8 = src.dtype == torch.uint8
-        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, self.path, self.B, part,
+        wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, self.path_blend, self.B, part,
                                               1 if part is not None else self.share)
         if items.shape[0] == 0:
             return
         p = self.plan
         src = src.contiguous()
         n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
-        flags = self.flags | (wl.block_rows << 8) | (wl.block_cols << 16)
+        flags = PATH_FLAGS[wl.path] | (wl.block_rows << 8) | (wl.block_cols << 16) | (nat.FLAG_MMA_KS2 if wl.ks2 else 0)
         target = self.buf.data_ptr()
         if canvas_ptr is not None and canvas_ptr != target:
             target, flags = canvas_ptr, flags | nat.FLAG_REMOTE_CANVAS

@@ -14,6 +14,7 @@ full-canvas PIL images; here it is computed once per job (and cached per geometr
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -177,6 +178,7 @@ class WorkList:
     block_cols: int = 0               # block width (generic kernels only)
     rows: Optional[Tuple[int, int]] = None   # blend with part=(i, n): canvas rows [y0, y1) of this share (whole block rows)
     path: int = 0                     # 0 generic work items, 1 fast job records, 2 tensor-core job records
+    ks2: bool = False                 # tensor-core records: some axis of the launch needs two k-steps (USDU_FLAG_MMA_KS2)
 
 
 @dataclass
@@ -505,7 +507,8 @@ class Plan:
         if not extents:
             return bw, nat.FAST_BLOCK_H
         best = None
-        for bh in ((16, 32) if mma else (8, 12, 16, 20, 24, 28, 32)):      # tensor-core M-tiles are 16 output rows
+        forced = os.environ.get("USDU_MMA_BH") if mma else None            # experiments: force the tensor-core block height
+        for bh in (((int(forced),) if forced else (16, 32)) if mma else (8, 12, 16, 20, 24, 28, 32)):   # M-tiles are 16 output rows
             n = sum(((w + bw - 1) // bw + 1) * ((h + bh - 1) // bh + 1) for w, h in extents) * frames   # +1: unaligned windows
             cost = math.ceil(n / max(self.SLOTS // max(share, 1), 1)) * (bh + 12)
             if best is None or cost < best[0] or (cost == best[0] and bh > best[1]):
@@ -593,8 +596,9 @@ class Plan:
         elif use_fast and items.shape[0]:
             items = self._crop_jobs(items)
         items = items.astype(np.uint32).view(np.int32) if items.size else items.astype(np.int32)
+        ks2 = bool(path == 2 and items.size and (items.reshape(-1, nat.JOB_WORDS)[:, [nat.J_TAPS_H, nat.J_TAPS_V]] > 1).any())
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes,
-                        block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw, path=path), offs, total
+                        block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw, path=path, ks2=ks2), offs, total
 
     # ---- tensor-core job records ---------------------------------------------------------
     def _mma_axis(self, key: Tuple[int, int], base: np.ndarray, extent: np.ndarray):
@@ -757,8 +761,9 @@ class Plan:
             jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh, path == 2)
             if path == 2:
                 jobs, pw_max, ph_max = jobs
+            ks2 = bool(path == 2 and (jobs[:, [nat.J_TAPS_H, nat.J_TAPS_V]] > 1).any())
             return WorkList(np.ascontiguousarray(jobs.astype(np.uint32).view(np.int32)), None, pw_max, ph_max, nbytes,
-                            n_launch=int(first.size), block_rows=bh, rows=rows, path=path)
+                            n_launch=int(first.size), block_rows=bh, rows=rows, path=path, ks2=ks2)
         cover = np.zeros((keys.size, nat.COVER_WORDS), dtype=np.int64)
         o = np.asarray(offs, dtype=np.int64)[seq]
         cover[:, 0], cover[:, 1], cover[:, 2] = tids, o & 0xFFFFFFFF, o >> 32

@@ -196,6 +196,8 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
  * patch_h = plane rows (multiple of 16) in bits 0..15, rows of the intermediate (multiple of 4) in bits 16..31.
  * usdu_tile_blend: block height 16 or 32 in flags bits 8..15. */
 #define USDU_FLAG_MMA 2
+/* ... some record of the launch has USDU_J_TAPS_H or _V == 2 (an axis scaled by more than ~1.4): run the two-k-step build */
+#define USDU_FLAG_MMA_KS2 4
 /* usdu_tile_blend with USDU_FLAG_FAST: bits 8..15 of `flags` carry the canvas block height the
  * job records were built for (1..USDU_FAST_BLOCK_H); the canvas block travels by TMA. */
 #define USDU_FLAG_BLOCK_ROWS(n) ((n) << 8)

@@ -15,7 +15,15 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("USDU_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """/root/reference in the build container; elsewhere the archive oracle/make_ref.py packed (oracle/_ref, git-ignored),
+    unpacked into a temporary directory."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import make_ref
+    return make_ref.staged_root() or "/root/reference"
+
+
+REF_ROOT = os.environ.get("USDU_REFERENCE_ROOT") or _default_root()
 PKG = "refpkg"
 
 

@@ -33,7 +33,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import usdu_oracle as orc  # noqa: E402
 
-REF_ROOT = os.environ.get("USDU_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """/root/reference in the build container; elsewhere the archive oracle/make_ref.py packed (oracle/_ref, git-ignored),
+    unpacked into a temporary directory."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import make_ref
+    return make_ref.staged_root() or "/root/reference"
+
+
+REF_ROOT = os.environ.get("USDU_REFERENCE_ROOT") or _default_root()
 PKG = "refstatic"
 
 ORDER = [
@@ -165,11 +173,13 @@ def torch_t0(pixels: torch.Tensor, seed: int, denoise: float) -> torch.Tensor:
 
 
 def run_static(image: np.ndarray, n_workers: int, tile: int, padding: int, mask_blur: int, uniform: bool,
-               seed: int, denoise: float, job_id: str = "job1", timeout: float = 600.0, master_delay: float = 0.0):
+               seed: int, denoise: float, job_id: str = "job1", timeout: float = 600.0, master_delay: float = 0.0,
+               max_tiles: int = 0):
     """-> (result fp32 [B,H,W,3] of the reference's master, assignment: list over participants
     (master first, then w1..wN) of the tile ids each one processed, in processing order).
     master_delay: seconds the master sleeps before each of its tiles, so that the workers (which
-    start later and talk HTTP) pull a fair share of the queue."""
+    start later and talk HTTP) pull a fair share of the queue.  max_tiles: every participant sees only the first
+    max_tiles tiles of the grid (the reference code is untouched: its calculate_tiles is wrapped on the node OBJECT)."""
     env = _Env()
     try:
         env.sampler = torch_t0
@@ -190,6 +200,9 @@ def run_static(image: np.ndarray, n_workers: int, tile: int, padding: int, mask_
                 return inner(upscaled_image, tx, ty, *rest)
 
             node.extract_batch_tile_with_padding = spy
+            if max_tiles > 0:                                   # bench.py's bounded sample: the job is the first max_tiles tiles
+                full = node.calculate_tiles
+                node.calculate_tiles = lambda *a, **k: full(*a, **k)[:max_tiles]
             return node
 
         x = torch.from_numpy(image)
