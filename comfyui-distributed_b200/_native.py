@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 6
+ABI_VERSION = 7
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -66,6 +66,8 @@ _SIGNATURES = {
     "usdu_box_blur_params": (c_int, [c_float, POINTER(c_int32), POINTER(c_uint32), POINTER(c_uint32)]),
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_gather_dequantize": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_tile_crop_resize_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "usdu_quantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "usdu_dequantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "usdu_pack_tiles_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -187,6 +189,19 @@ def quantize_rows(img_ptr, canvas_ptr, B, H, W, pitch, y0, y1, stream):
 
 def dequantize_rows(canvas_ptr, img_ptr, B, H, W, pitch, y0, y1, stream):
     _check(lib().usdu_dequantize_rows(canvas_ptr, img_ptr, B, H, W, pitch, y0, y1, stream), "usdu_dequantize_rows")
+
+
+def gather_dequantize(slab_ptrs, slab_rows, img_ptr, B, H, W, pitch, stream):
+    """slab_ptrs: device addresses of the n canvases; slab_rows: n + 1 row boundaries (0 .. H)."""
+    n = len(slab_ptrs)
+    ptrs = (ctypes.c_void_p * n)(*[int(p) for p in slab_ptrs])
+    rows = (c_int32 * (n + 1))(*[int(r) for r in slab_rows])
+    _check(lib().usdu_gather_dequantize(ptrs, rows, n, img_ptr, B, H, W, pitch, stream), "usdu_gather_dequantize")
+
+
+def tile_crop_resize_f32(image_ptr, B, H, W, tabs_ptr, items_ptr, n_items, patch_w, patch_h, out_ptr, flags, stream):
+    _check(lib().usdu_tile_crop_resize_f32(image_ptr, B, H, W, tabs_ptr, items_ptr, n_items, patch_w, patch_h, out_ptr, flags, stream),
+           "usdu_tile_crop_resize_f32")
 
 
 def dequantize_canvas(canvas_ptr, img_ptr, B, H, W, pitch, stream):

@@ -80,6 +80,51 @@ dequantize_canvas_kernel(const uint8_t* __restrict__ canvas, float* __restrict__
     }
 }
 
+// The master's gather of a multi-GPU job: canvas rows [y[q], y[q+1]) come from slab q's canvas (base[q] -- a peer's HBM
+// mapped over NVLink, or the local one), every row is dequantised into the local fp32 result.  A CTA moves 4 KB of a row:
+// 16-byte loads (few, wide requests on the link), a shared-memory turn, whole-sector float4 stores.
+struct GatherArgs {
+    const uint8_t* base[USDU_MAX_SLABS];
+    int y[USDU_MAX_SLABS + 1];
+    int n;
+};
+
+__global__ void __launch_bounds__(kThreads)
+gather_dequantize_kernel(GatherArgs a, float* __restrict__ img, int rows_total, int H, int W3, int64_t pitch) {
+    __shared__ uint4 stage[kThreads];
+    const int c0 = blockIdx.x * (kThreads * 16);                 // first byte of this CTA's chunk of the row
+    for (int lrow = blockIdx.y; lrow < rows_total; lrow += gridDim.y) {
+        const int fb = lrow / H, yy = lrow - fb * H;
+        int q = 0;
+        while (q + 1 < a.n && yy >= a.y[q + 1]) ++q;
+        const uint8_t* src = a.base[q] + ((int64_t)fb * H + yy) * pitch + c0;
+        const int off = threadIdx.x * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c0 + off + 16 <= W3) v = __ldcs(reinterpret_cast<const uint4*>(src + off));
+        else if (c0 + off < W3) {                                 // row tail (W3 % 16 != 0): word loads, W3 % 4 == 0
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) if (c0 + off + 4 * k < W3) w[k] = __ldcs(reinterpret_cast<const uint32_t*>(src + off) + k);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncthreads();                                          // the previous row's readers are done
+        stage[threadIdx.x] = v;
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(img + ((int64_t)fb * H + yy) * W3 + c0);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(stage);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int wi = k * kThreads + threadIdx.x;            // consecutive lanes -> consecutive float4
+            if (c0 + 4 * wi < W3) {
+                const uint32_t u = words[wi];
+                float4 o;
+                o.x = dequant_u8_fast(u & 0xFF); o.y = dequant_u8_fast((u >> 8) & 0xFF);
+                o.z = dequant_u8_fast((u >> 16) & 0xFF); o.w = dequant_u8_fast(u >> 24);
+                __stcs(dst + wi, o);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 pack_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
     const int64_t n16 = n >> 4;
@@ -449,8 +494,8 @@ int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int3
 } }
 
 namespace usdu { namespace mma {
-int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
-                int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st);
+int launch_crop(const void* canvas, int src_f32, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items,
+                int n_items, int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st);
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
                  const int32_t* items, int n_items, int patch_w, int patch_h, const void* src, int src_is_u8, int block_rows,
                  int two_ksteps, cudaStream_t st);
@@ -499,6 +544,39 @@ int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H
     if (gy * gx > 148 * 16) gy = (148 * 16 + gx - 1) / gx;
     if (gy < 1) gy = 1;
     dequantize_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * (y1 - y0), W3, pitch, vec_ok, H, y0, y1 - y0);
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+int usdu_gather_dequantize(const uint8_t* const* slab_canvas_dev, const int32_t* slab_rows, int n_slabs, float* img_dev,
+                           int B, int H, int W, int64_t pitch, void* stream) {
+    USDU_REQUIRE(slab_canvas_dev && slab_rows && img_dev, "usdu_gather_dequantize: null pointer");
+    USDU_REQUIRE(n_slabs >= 1 && n_slabs <= USDU_MAX_SLABS, "usdu_gather_dequantize: 1..%d slabs, got %d", USDU_MAX_SLABS, n_slabs);
+    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_gather_dequantize: bad shape %dx%dx%d", B, H, W);
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_gather_dequantize: pitch %lld must be >= 3*W and a multiple of 16", (long long)pitch);
+    USDU_REQUIRE(slab_rows[0] == 0 && slab_rows[n_slabs] == H, "usdu_gather_dequantize: the slabs must tile rows 0..%d", H);
+    const int W3 = W * 3;
+    bool vec = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0);
+    GatherArgs a;
+    a.n = n_slabs;
+    for (int q = 0; q < n_slabs; ++q) {
+        USDU_REQUIRE(slab_canvas_dev[q] != nullptr && slab_rows[q] <= slab_rows[q + 1], "usdu_gather_dequantize: bad slab %d", q);
+        a.base[q] = slab_canvas_dev[q];
+        a.y[q] = slab_rows[q];
+        vec = vec && (((uintptr_t)slab_canvas_dev[q] & 15) == 0);
+    }
+    a.y[n_slabs] = H;
+    if (!vec) {                                   // odd widths: slab by slab through the scalar path
+        for (int q = 0; q < n_slabs; ++q) {
+            int s = usdu_dequantize_rows(slab_canvas_dev[q], img_dev, B, H, W, pitch, slab_rows[q], slab_rows[q + 1], stream);
+            if (s != USDU_OK) return s;
+        }
+        return USDU_OK;
+    }
+    const int gx = (W3 + kThreads * 16 - 1) / (kThreads * 16);
+    int64_t gy = (int64_t)B * H;
+    if (gy > 65535) gy = 65535;
+    gather_dequantize_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(a, img_dev, B * H, H, W3, pitch);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }
@@ -627,7 +705,7 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
     USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0, "usdu_tile_crop_resize: pitch must be >= 3*W and a multiple of 16");
     if (flags & USDU_FLAG_MMA) {
         USDU_REQUIRE(tabs_dev != nullptr, "usdu_tile_crop_resize: tensor-core path needs tables");
-        return mma::launch_crop(canvas_dev, B, H, W, pitch, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev,
+        return mma::launch_crop(canvas_dev, 0, B, H, W, pitch, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev,
                                 (flags & USDU_FLAG_MMA_KS2) ? 1 : 0, (cudaStream_t)stream);
     }
     if (flags & USDU_FLAG_FAST) {
@@ -646,6 +724,16 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
         canvas_dev, H, W, pitch, tiles_dev, tabs_dev, items_dev, out_dev, in_pitch, patch_h, blk_w, blk_h);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
+}
+
+int usdu_tile_crop_resize_f32(const float* image_dev, int B, int H, int W, const int32_t* tabs_dev, const int32_t* items_dev,
+                              int n_items, int patch_w, int patch_h, float* out_dev, int flags, void* stream) {
+    USDU_REQUIRE(image_dev && tabs_dev && items_dev && out_dev, "usdu_tile_crop_resize_f32: null pointer");
+    USDU_REQUIRE(B > 0 && H > 0 && W > 0 && n_items >= 0 && B <= 65535, "usdu_tile_crop_resize_f32: bad shape");
+    USDU_REQUIRE(flags & USDU_FLAG_MMA, "usdu_tile_crop_resize_f32: tensor-core job records only (USDU_FLAG_MMA)");
+    if (n_items == 0) return USDU_OK;
+    return mma::launch_crop(image_dev, 1, B, H, W, (int64_t)W * 3, tabs_dev, items_dev, n_items, patch_w, patch_h, out_dev,
+                            (flags & USDU_FLAG_MMA_KS2) ? 1 : 0, (cudaStream_t)stream);
 }
 
 int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, const int32_t* tiles_dev,

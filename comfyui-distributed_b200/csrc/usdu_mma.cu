@@ -330,13 +330,17 @@ struct CropEpilogue {
     }
 };
 
-template <bool kTma, int KSMAX>
+// kSrc: 0 = u8 canvas read with LDG, 1 = u8 canvas staged by TMA, 2 = the fp32 IMAGE itself (`canvas` is then a float
+// pointer and `pitch` counts floats per row): Q0's truncating cast happens while staging, the window is bit-identical
+// to cropping the quantised canvas -- a rank of a conflict-free partition never needs the quantised canvas at all.
+template <int kSrc, int KSMAX>
 __global__ void __launch_bounds__(kT, KSMAX == 1 ? USDU_MMA_CTAS : 3)
 crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int plane_rows, int mid_rows, int W3,
                 const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job] [lut] [bar] [planes]
+    constexpr bool kTma = kSrc == 1;
     const size_t region = kTma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
     uint32_t* mid = reinterpret_cast<uint32_t*>(smem);
     uint8_t* raw = smem;
@@ -364,6 +368,9 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
         }
         tma::mbar_wait(bar, 0);
         stage_raw(planes, PB, plane_rows, raw, J[USDU_J_ROWS], J[USDU_J_COLS], sa3 & 15);
+    } else if (kSrc == 2) {
+        const float* src = reinterpret_cast<const float*>(canvas) + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + sa3;
+        stage_f32(planes, PB, plane_rows, src, pitch, J[USDU_J_ROWS], J[USDU_J_COLS]);
     } else {
         const uint8_t* src = canvas + ((int64_t)b * H + J[USDU_J_SRC_B]) * pitch + sa3;
         stage_u8(planes, PB, plane_rows, src, pitch, J[USDU_J_ROWS], J[USDU_J_COLS]);
@@ -552,24 +559,34 @@ static int launch_one(K kernel, size_t smem, dim3 grid, cudaStream_t st, Args...
     return USDU_OK;
 }
 
-int launch_crop(const uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items, int n_items,
-                int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st) {
+int launch_crop(const void* canvas, int src_f32, int B, int H, int W, int64_t pitch, const int32_t* tabs, const int32_t* items,
+                int n_items, int patch_w, int patch_h, float* out, int two_ksteps, cudaStream_t st) {
     int plane_rows, mid_rows;
     int s = split_patch_h(patch_h, &plane_rows, &mid_rows, "usdu_tile_crop_resize");
     if (s != USDU_OK) return s;
     CUtensorMap cmap;
     memset(&cmap, 0, sizeof(cmap));
+    const uint8_t* cv = static_cast<const uint8_t*>(canvas);
+    const dim3 grid(n_items, B);
+    const int W3 = W * 3;
+    if (src_f32) {
+        if (W % 4 != 0 || ((uintptr_t)canvas & 15) != 0) {
+            set_error("usdu_tile_crop_resize_f32: the image width must be a multiple of 4 and the image 16-byte aligned");
+            return USDU_ERR_UNSUPPORTED;
+        }
+        const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, false);
+        return two_ksteps ? launch_one(crop_mma_kernel<2, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
+                          : launch_one(crop_mma_kernel<2, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+    }
     // TMA staging needs the patch to fit the two boxes (the planner keeps the staged rows <= 48 for scales <= ~1.2)
     bool use_tma = plane_rows <= kBoxR && 12 + patch_w * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
     if (use_tma) use_tma = tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kBoxB, kBoxR);
     const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, use_tma);
-    const dim3 grid(n_items, B);
-    const int W3 = W * 3;
     if (use_tma)
-        return two_ksteps ? launch_one(crop_mma_kernel<true, 2>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
-                          : launch_one(crop_mma_kernel<true, 1>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
-    return two_ksteps ? launch_one(crop_mma_kernel<false, 2>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
-                      : launch_one(crop_mma_kernel<false, 1>, smem, grid, st, canvas, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+        return two_ksteps ? launch_one(crop_mma_kernel<1, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
+                          : launch_one(crop_mma_kernel<1, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+    return two_ksteps ? launch_one(crop_mma_kernel<0, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
+                      : launch_one(crop_mma_kernel<0, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
 }
 
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,

@@ -210,10 +210,13 @@ class StaticJob:
         # with a conflict-free partition no crop of this rank ever sees one of its own blends and, when the final
         # canvas is composited slab by slab from the payloads, nobody reads this rank's working canvas: skip them
         self.skip = ("blend",) if (self.sharded and self.conflict_free) else ()
+        # ... and then its crops can read the fp32 image directly: the whole-canvas quantise (90 us of every rank's step on
+        # the 8K canvas, never sharded) disappears from the device-resident path
+        self.from_image = bool(self.skip) and Canvas(self.dp, B, self.work_buf).can_crop_image() and len(self.asg[self.rank]) > 0
         self.gw = None
         if self.graphed:
             self.gw = _eng.GraphedWaves.get(self.dp, B, denoiser, _eng.PROFILE, order=self.asg[self.rank], payload=self.payload,
-                                            where=self.where, canvas_buf=self.work_buf, skip=self.skip)
+                                            where=self.where, canvas_buf=self.work_buf, skip=self.skip, external_crop=self.from_image)
         self.final_canvas = None
         self.rows = None
         if self.sharded:
@@ -243,10 +246,24 @@ class StaticJob:
     def run_tiles(self, image: Optional[torch.Tensor], denoiser, resident: bool = False):
         """Phase A: this rank's tiles (crop -> sampler -> local blend -> u8 pack into the payload).  resident: the
         working canvas already holds the quantised input (host path: gathered slabs)."""
-        from .engine import Canvas, run_progressive
+        from .engine import Canvas, run_progressive, _sorted_by_shape
         if self.gw is not None:
-            return self.gw.replay(image) if not resident else self.gw.replay_resident()
+            if resident:                         # (host path: the working canvas holds the gathered u8 slabs; crop from it)
+                if self.from_image:
+                    c = self.gw.canvas
+                    c.launches, c.algo_bytes = self.gw.launches_per_replay, self.gw.bytes_per_replay
+                    c.crop(self.gw.crop_tiles, out=self.gw.crop_buf)
+                    self.gw.graph.replay()
+                    return c
+                return self.gw.replay_resident()
+            return self.gw.replay_from_image(image) if self.from_image else self.gw.replay(image)
         canvas = Canvas(self.dp, self.B, self.work_buf)
+        if self.from_image and not resident:
+            tiles = _sorted_by_shape(self.plan, self.plan.waves(self.asg[self.rank])[0])
+            buf, _ = canvas.crop(tiles, image=image)
+            run_progressive(canvas, self.asg[self.rank], denoiser, payload=self.payload, where=self.where,
+                            skip=tuple(set(self.skip) | {"crop"}), crop_buf=buf)
+            return canvas
         if not resident:
             canvas.load(image)
         run_progressive(canvas, self.asg[self.rank], denoiser, payload=self.payload, where=self.where, skip=self.skip)
@@ -270,11 +287,11 @@ class StaticJob:
         from . import _native as nat
         from .engine import _stream_ptr
         p, c = self.plan, self.final_canvas
-        for q in range(self.world):
-            y0, y1 = self.rows[q]
-            if y1 > y0:
-                nat.dequantize_rows(self.final.ptrs[q], out.data_ptr(), self.B, p.H, p.W, c.pitch, y0, y1, _stream_ptr())
-                c.launches += 1
+        live = [q for q in range(self.world) if self.rows[q][1] > self.rows[q][0]]
+        bounds = [0] + [self.rows[q][1] for q in live]
+        bounds[-1] = p.H
+        nat.gather_dequantize([self.final.ptrs[q] for q in live], bounds, out.data_ptr(), self.B, p.H, p.W, c.pitch, _stream_ptr())
+        c.launches += 1
 
 
 def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int,

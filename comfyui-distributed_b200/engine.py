@@ -189,11 +189,33 @@ class Canvas:
         return self.buf[:, :, : self.plan.W * 3].reshape(self.B, self.plan.H, self.plan.W, 3)
 
     # K2 (tile_ops.py:96-155)
-    def crop(self, tile_ids: Sequence[int], out: Optional[torch.Tensor] = None):
+    def can_crop_image(self) -> bool:
+        """The tensor-core crop can read the fp32 image itself (usdu_tile_crop_resize_f32)."""
+        return self.path_crop == 2 and self.plan.W % 4 == 0
+
+    def crop(self, tile_ids: Sequence[int], out: Optional[torch.Tensor] = None, image: Optional[torch.Tensor] = None):
         """-> (flat fp32 buffer, element offsets per tile).  Tile i is
-        buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3)."""
+        buffer[offs[i] : offs[i] + B*ph*pw*3].view(B, ph, pw, 3).
+        image: crop the windows straight from this fp32 image [B,H,W,3] instead of the canvas (identical tiles as long
+        as the canvas still is the quantised image there: a conflict-free partition, dist.StaticJob)."""
         tile_ids = tuple(int(t) for t in tile_ids)
         wl, offs, total, items, _ = self.dp.crop_list(tile_ids, self.B, self.path_crop, self.share)
+        if image is not None:
+            if not (self.can_crop_image() and wl.path == 2):
+                raise nat.NativeError("crop from the fp32 image needs the tensor-core kernels and a canvas width that is a multiple of 4")
+            _require_cuda(image, "image")
+            if tuple(image.shape) != (self.B, self.plan.H, self.plan.W, 3) or image.dtype != torch.float32 or not image.is_contiguous():
+                raise ValueError("crop: image must be contiguous float32 [B,H,W,3] of the plan's size")
+            if out is None:
+                out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
+            p = self.plan
+            _launch("crop_resize", (wl.algo_bytes + 9 * sum(p.tiles[t].ew * p.tiles[t].eh for t in tile_ids)) * self.B,
+                    lambda: nat.tile_crop_resize_f32(image.data_ptr(), self.B, p.H, p.W, self.dp.tabs.data_ptr(), items.data_ptr(),
+                                                     items.shape[0], wl.patch_w, wl.patch_h, out.data_ptr(),
+                                                     PATH_FLAGS[2] | (nat.FLAG_MMA_KS2 if wl.ks2 else 0), _stream_ptr()))
+            self.launches += 1
+            self.algo_bytes += wl.algo_bytes * self.B
+            return out, offs
         if out is None:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
@@ -292,7 +314,8 @@ def processing_order(plan: Plan, tile_ids: Sequence[int]) -> List[int]:
 
 
 def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, keep_processed: bool = False,
-                    payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = ()):
+                    payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = (),
+                    crop_buf: Optional[torch.Tensor] = None):
     """Process `order` (tile ids) with the reference's progressive semantics on `canvas`
     (single_gpu.py:40-64 / static.py:242-280): wave by wave, each wave = crop kernel,
     one sampler call, blend kernel.  What a static-mode worker ships to the master (the
@@ -303,7 +326,10 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     scratch = None
     for wave in plan.waves(order):
         wave = _sorted_by_shape(plan, wave)
-        if "crop" in skip:      # bench.py's differencing measurement: same graph minus one kernel kind
+        if "crop" in skip and crop_buf is not None:    # the caller cropped this (single) wave itself: GraphedWaves.replay_from_image
+            offs, total = plan.slot_offsets(wave, B)
+            buf = crop_buf[:total]
+        elif "crop" in skip:    # bench.py's differencing measurement: same graph minus one kernel kind
             offs, total = plan.slot_offsets(wave, B)
             if scratch is None or scratch.numel() < total:
                 scratch = torch.zeros(total, dtype=torch.float32, device=canvas.buf.device)
@@ -405,11 +431,21 @@ class GraphedWaves:
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
                  order: Optional[Sequence[int]] = None, keep_processed: bool = False,
                  payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = (),
-                 canvas_buf: Optional[torch.Tensor] = None):
+                 canvas_buf: Optional[torch.Tensor] = None, external_crop: bool = False):
         global PROFILE
         self.canvas = Canvas(dp, B, canvas_buf)
         self.denoiser = denoiser
         order = list(range(len(dp.plan.tiles))) if order is None else list(order)
+        # external_crop: the tiles (ONE wave: a conflict-free share) are cropped by the caller from the fp32 image right
+        # before every replay; the graph starts at the sampler
+        self.crop_tiles, self.crop_buf = None, None
+        if external_crop:
+            waves = dp.plan.waves(order)
+            if len(waves) != 1 or not self.canvas.can_crop_image():
+                raise ValueError("external_crop needs a single wave and the tensor-core crop")
+            self.crop_tiles = _sorted_by_shape(dp.plan, waves[0])
+            self.crop_buf = torch.zeros(dp.plan.slot_offsets(self.crop_tiles, B)[1], dtype=torch.float32, device=dp.device)
+            skip = tuple(set(skip) | {"crop"})
         self.shipped: Dict[int, torch.Tensor] = {}
         self.payload = payload        # caller-owned transport buffer the packed u8 tiles are written into
         self.canvas.buf.zero_()
@@ -425,7 +461,7 @@ class GraphedWaves:
             if self.dag:
                 run_dag(self.canvas, order, denoiser, lanes, self.payload, where, skip)
                 return {}
-            return run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip)
+            return run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip, self.crop_buf)
 
         with torch.cuda.stream(side):                 # warm-up: fills every cache (work lists, noise)
             body()
@@ -451,17 +487,17 @@ class GraphedWaves:
     def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile] = None,
             order: Optional[Sequence[int]] = None, keep_processed: bool = False,
             payload: Optional[torch.Tensor] = None, where: Optional[dict] = None, skip: Sequence[str] = (),
-            canvas_buf: Optional[torch.Tensor] = None) -> "GraphedWaves":
+            canvas_buf: Optional[torch.Tensor] = None, external_crop: bool = False) -> "GraphedWaves":
         pkey = None if payload is None else (payload.data_ptr(), payload.numel())
         ckey = None if canvas_buf is None else canvas_buf.data_ptr()
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE,
-               None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey)
+               None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey, external_crop)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:
             if len(cls._cache) > 6:
                 cls._cache.clear()
             gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip,
-                                                canvas_buf)
+                                                canvas_buf, external_crop)
         return gw
 
     def replay(self, image: torch.Tensor) -> Canvas:
@@ -469,6 +505,15 @@ class GraphedWaves:
         c = self.canvas
         c.launches, c.algo_bytes = self.launches_per_replay, self.bytes_per_replay
         c.load(image)
+        self.graph.replay()
+        return c
+
+    def replay_from_image(self, image: torch.Tensor) -> Canvas:
+        """external_crop: one eager crop launch straight from the caller's fp32 image (no quantised canvas at all), then
+        the captured sampler + pack."""
+        c = self.canvas
+        c.launches, c.algo_bytes = self.launches_per_replay, self.bytes_per_replay
+        c.crop(self.crop_tiles, out=self.crop_buf, image=image)
         self.graph.replay()
         return c
 

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 6
+#define USDU_ABI_VERSION 7
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -225,6 +225,14 @@ int usdu_quantize_rows(const float* img_dev, uint8_t* canvas_dev, int B, int H, 
                        int y0, int y1, void* stream);
 int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H, int W, int64_t pitch,
                          int y0, int y1, void* stream);
+/* The master's gather of a multi-GPU job in ONE launch: canvas rows [slab_rows[q], slab_rows[q+1]) are read from
+ * slab_canvas_dev[q] (host array of n_slabs device pointers, each the base of a whole [B][H][pitch] canvas: the local one
+ * or a peer's mapped over NVLink) and dequantised into the local fp32 image.  slab_rows (host, n_slabs + 1 ints) must
+ * start at 0 and end at H.  Replaces the master's drain loop + result conversion, upscale/result_collector.py:36-182 and
+ * upscale/modes/static.py:556-564. */
+#define USDU_MAX_SLABS 16
+int usdu_gather_dequantize(const uint8_t* const* slab_canvas_dev, const int32_t* slab_rows, int n_slabs,
+                           float* img_dev, int B, int H, int W, int64_t pitch, void* stream);
 /* Q1 for transport: dst[i] = (uint8)(255.f * src[i]); n elements (worker_comms.py:30-33) */
 int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* stream);
 /* receiving side of the transport: dst[i] = src[i] / 255.0f (api/job_routes.py:104-132) */
@@ -250,6 +258,14 @@ int usdu_tile_crop_resize(const uint8_t* canvas_dev, int B, int H, int W, int64_
                           const int32_t* tiles_dev, const int32_t* tabs_dev,
                           const int32_t* items_dev, int n_items, int patch_w, int patch_h,
                           float* out_dev, int flags, void* stream);
+
+/* The same crop straight from the fp32 IMAGE [B][H][W][3] (tensor-core job records only, W % 4 == 0): the truncating
+ * cast of utils/image.py:8-10 happens while the window is staged, the tiles are bit-identical to cropping the
+ * quantised canvas.  For participants whose tiles never overlap (a conflict-free static partition: every crop of
+ * upscale/modes/static.py:242-280 then sees the ORIGINAL image), which therefore never need the quantised canvas. */
+int usdu_tile_crop_resize_f32(const float* image_dev, int B, int H, int W, const int32_t* tabs_dev,
+                              const int32_t* items_dev, int n_items, int patch_w, int patch_h,
+                              float* out_dev, int flags, void* stream);
 
 /* Seam blend: for every item (canvas block) apply its cover list in order:
  * quantise (fp32 source) -> LANCZOS back to the crop size -> integer alpha composite

@@ -141,6 +141,32 @@ def test_static_mode_result_on_all_ranks():
     _run(_w_all_ranks, 2)
 
 
+def _w_conflict_free(rank, world):
+    """A partition without overlapping windows inside a rank: the ranks crop straight from the fp32 image (no quantised
+    working canvas, usdu_tile_crop_resize_f32), skip their local blends, and the final canvas is composited slab by slab."""
+    from comfyui_distributed_b200 import dist as udist
+    from comfyui_distributed_b200.denoise import T0Denoiser
+    B, H, W, tile, pad, blur = 2, 256, 1280, 256, 32, 8
+    asg = [[0, 2, 4], [1, 3]]
+    for job in range(3):
+        img = make_input("noise", 41 + job, B, H, W)
+        x = torch.from_numpy(img).cuda()
+        st = {}
+        out = udist.upscale_static(x, T0Denoiser(9, 0.5), tile, tile, pad, blur, True, assignment=asg, stats=st)
+        assert st["conflict_free"] and st["final_blend"].startswith("sharded")
+        job_obj = list(udist.StaticJob._cache.values())[-1]
+        assert job_obj.from_image, "expected the crop-from-image path (tensor-core plan, W % 4 == 0)"
+        if rank == 0:
+            ref = orc.replay_static(img, orc.make_t0_denoiser(9, 0.5), tile, tile, pad, blur, True, asg)
+            assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_conflict_free_partition_crops_from_the_image():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(_w_conflict_free, 2)
+
+
 def _w_host(rank, world, case):
     """dist.upscale_static_host: every rank uploads / downloads only its slab; the result tensor lives in shared
     page-locked memory.  Several jobs in a row: held results must not be overwritten, dropped ones are recycled."""
