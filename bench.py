@@ -465,6 +465,20 @@ def main():
     e2e_ms = float(t.item())
     clk = clocks.stop()
     img_bytes = B * H * W * 3 * 4
+    e2e_phases = None
+    if world > 1:                                        # where the end-to-end call goes, per phase, max over ranks
+        acc = {}
+        for _ in range(5):
+            node.time_phases = True
+            step_e2e()
+            for k_, v_ in (node.last_stats.get("phase_ms") or {}).items():
+                acc.setdefault(k_, []).append(v_)
+        node.time_phases = False
+        if acc:
+            names = list(acc)
+            t = torch.tensor([sorted(acc[n_])[len(acc[n_]) // 2] for n_ in names], device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            e2e_phases = {n_: round(float(v_), 4) for n_, v_ in zip(names, t.tolist())}
 
     # ---- supplementary: the same job with an SDXL-cost sampler (T1), one timed step -----------
     t1_info = None
@@ -537,6 +551,8 @@ def main():
             "roofline": roofline}
     if phases is not None:
         line["phase_ms_max_over_ranks"] = phases
+    if e2e_phases is not None:
+        line["e2e"]["phase_ms_max_over_ranks"] = e2e_phases
     if t1_info is not None:
         line["sdxl_cost_tier"] = t1_info
     if not args.no_cpu_baseline and world == 1:

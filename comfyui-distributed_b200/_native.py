@@ -67,6 +67,7 @@ _SIGNATURES = {
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_gather_dequantize": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_gather_canvas": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_tile_crop_resize_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "usdu_quantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "usdu_dequantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
@@ -197,6 +198,13 @@ def gather_dequantize(slab_ptrs, slab_rows, img_ptr, B, H, W, pitch, stream):
     ptrs = (ctypes.c_void_p * n)(*[int(p) for p in slab_ptrs])
     rows = (c_int32 * (n + 1))(*[int(r) for r in slab_rows])
     _check(lib().usdu_gather_dequantize(ptrs, rows, n, img_ptr, B, H, W, pitch, stream), "usdu_gather_dequantize")
+
+
+def gather_canvas(slab_ptrs, slab_rows, canvas_ptr, B, H, W, pitch, stream):
+    n = len(slab_ptrs)
+    ptrs = (ctypes.c_void_p * n)(*[int(p) for p in slab_ptrs])
+    rows = (c_int32 * (n + 1))(*[int(r) for r in slab_rows])
+    _check(lib().usdu_gather_canvas(ptrs, rows, n, canvas_ptr, B, H, W, pitch, stream), "usdu_gather_canvas")
 
 
 def tile_crop_resize_f32(image_ptr, B, H, W, tabs_ptr, items_ptr, n_items, patch_w, patch_h, out_ptr, flags, stream):

@@ -125,6 +125,22 @@ gather_dequantize_kernel(GatherArgs a, float* __restrict__ img, int rows_total, 
     }
 }
 
+// ... and the all-gather of the quantised INPUT slabs (host path: every rank uploads and quantises 1/N of the rows, then
+// pulls the other N-1 slabs into its own working canvas): the same walk, bytes copied as they are, 16 per thread.
+__global__ void __launch_bounds__(kThreads)
+gather_canvas_kernel(GatherArgs a, uint8_t* __restrict__ dst, int rows_total, int H, int row_bytes, int64_t pitch) {
+    const int off = (blockIdx.x * kThreads + threadIdx.x) * 16;
+    if (off >= row_bytes) return;
+    for (int lrow = blockIdx.y; lrow < rows_total; lrow += gridDim.y) {
+        const int fb = lrow / H, yy = lrow - fb * H;
+        int q = 0;
+        while (q + 1 < a.n && yy >= a.y[q + 1]) ++q;
+        const int64_t at = ((int64_t)fb * H + yy) * pitch + off;
+        if (a.base[q] == dst) continue;                            // this rank's own slab is already in place
+        *reinterpret_cast<uint4*>(dst + at) = __ldcs(reinterpret_cast<const uint4*>(a.base[q] + at));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 pack_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
     const int64_t n16 = n >> 4;
@@ -577,6 +593,31 @@ int usdu_gather_dequantize(const uint8_t* const* slab_canvas_dev, const int32_t*
     int64_t gy = (int64_t)B * H;
     if (gy > 65535) gy = 65535;
     gather_dequantize_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(a, img_dev, B * H, H, W3, pitch);
+    USDU_CUDA(cudaGetLastError());
+    return USDU_OK;
+}
+
+int usdu_gather_canvas(const uint8_t* const* slab_canvas_dev, const int32_t* slab_rows, int n_slabs, uint8_t* canvas_dev,
+                       int B, int H, int W, int64_t pitch, void* stream) {
+    USDU_REQUIRE(slab_canvas_dev && slab_rows && canvas_dev, "usdu_gather_canvas: null pointer");
+    USDU_REQUIRE(n_slabs >= 1 && n_slabs <= USDU_MAX_SLABS, "usdu_gather_canvas: 1..%d slabs, got %d", USDU_MAX_SLABS, n_slabs);
+    USDU_REQUIRE(B > 0 && H > 0 && W > 0, "usdu_gather_canvas: bad shape %dx%dx%d", B, H, W);
+    USDU_REQUIRE(pitch >= 3LL * W && pitch % 16 == 0 && ((uintptr_t)canvas_dev & 15) == 0, "usdu_gather_canvas: pitch / base must be multiples of 16");
+    USDU_REQUIRE(slab_rows[0] == 0 && slab_rows[n_slabs] == H, "usdu_gather_canvas: the slabs must tile rows 0..%d", H);
+    GatherArgs a;
+    a.n = n_slabs;
+    for (int q = 0; q < n_slabs; ++q) {
+        USDU_REQUIRE(slab_canvas_dev[q] != nullptr && ((uintptr_t)slab_canvas_dev[q] & 15) == 0 && slab_rows[q] <= slab_rows[q + 1],
+                     "usdu_gather_canvas: bad slab %d", q);
+        a.base[q] = slab_canvas_dev[q];
+        a.y[q] = slab_rows[q];
+    }
+    a.y[n_slabs] = H;
+    const int row_bytes = (W * 3 + 15) / 16 * 16;                // whole 16-byte words of a row (<= pitch)
+    const int gx = (row_bytes / 16 + kThreads - 1) / kThreads;
+    int64_t gy = (int64_t)B * H;
+    if (gy > 65535) gy = 65535;
+    gather_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(a, canvas_dev, B * H, H, row_bytes, pitch);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
 }

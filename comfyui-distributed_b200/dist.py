@@ -387,6 +387,36 @@ def upscale_static(image: torch.Tensor, denoiser, tile_width: int, tile_height: 
 # --------------------------------------------------------------------------------------
 # static mode on HOST tensors: every rank moves 1/N of the image over ITS OWN PCIe link
 # --------------------------------------------------------------------------------------
+class _near_gpu_cpus:
+    """Context: run on the CPUs next to this process's current GPU (NVML's affinity mask) -- used for first-touch page
+    placement only; silently a no-op when NVML or sched_setaffinity is unavailable."""
+
+    def __enter__(self):
+        self.saved = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(torch.cuda.current_device()).uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            n_words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+            cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+            if cpus:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, cpus & self.saved or cpus)
+        except Exception:        # noqa: BLE001 -- placement is an optimisation
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:    # noqa: BLE001
+                pass
+        return False
+
+
 class SharedHost:
     """Result buffers in POSIX shared memory, page-locked (cudaHostRegister) in every rank's process, plus a small
     control block for host-side hand-shakes.  The reference's workers each hold the whole canvas and the master alone
@@ -433,18 +463,25 @@ class SharedHost:
                 pass
         self.paths = []
 
-    def _map(self, numel: int, k: int) -> torch.Tensor:
-        """Buffer k of `numel` floats: mapped and page-locked on first use (~150 ms for 400 MB, once)."""
+    def _map(self, numel: int, k: int, touch: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """Buffer k of `numel` floats: mapped and page-locked on first use (~150 ms for 400 MB, once).  touch = (a, b):
+        element range this rank will write -- it is first-touched here, COLLECTIVELY (every rank maps a new buffer in the
+        same job, see begin())."""
         lst = self.bufs.setdefault(numel, [])
         while len(lst) <= k:
             lst.append(None)
         if lst[k] is None:
             path = self._path(f"{numel}_{k}")
-            if self.rank == 0:
-                with open(path, "wb") as f:
-                    f.truncate(numel * 4)
-                self.paths.append(path)
             t = torch.from_file(path, shared=True, size=numel, dtype=torch.float32)
+            if touch is not None:
+                # First touch decides which NUMA node a page of the shared buffer lives on.  Every rank touches the rows IT
+                # will download into, on a CPU next to its GPU: otherwise all pages sit next to rank 0 and the GPUs of the
+                # other socket write across the inter-socket link (measured on this 2-socket box: 4.2 ms instead of ~1 ms
+                # for a 50 MB slab with 4 of 8 GPUs on the far socket).
+                a, b = touch
+                with _near_gpu_cpus():
+                    t.view(-1)[a:b].zero_()
+                td.barrier(group=self.group)
             err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * 4, 0)
             if int(err) != 0:
                 raise RuntimeError(f"cudaHostRegister of the shared result buffer failed: {err}")
@@ -458,9 +495,10 @@ class SharedHost:
             if time.perf_counter() - t0 > 120.0:
                 raise RuntimeError(f"shared-host hand-shake timed out waiting for {what}")
 
-    def begin(self, shape) -> torch.Tensor:
+    def begin(self, shape, touch: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """Collective (host side only): the result tensor of the next job, the same physical pages on every rank.
-        Rank 0 picks a buffer nobody references any more (engine.buffer_is_unreferenced) or maps a new one."""
+        Rank 0 picks a buffer nobody references any more (engine.buffer_is_unreferenced) or maps a new one.
+        touch: flat element range of the result this rank writes (NUMA placement of a new buffer, see _map)."""
         from .engine import buffer_is_unreferenced
         numel = int(np.prod(shape))
         self.job += 1
@@ -472,14 +510,18 @@ class SharedHost:
                 if lst[i] is not None and buffer_is_unreferenced(lst[i]):
                     k = i
                     break
-            buf = self._map(numel, k)          # the file exists before the index is published
             if k < have and torch.cuda.is_available():
                 torch.cuda.synchronize()       # copies a consumer may have queued out of a recycled buffer
+            if k >= have:                      # a new buffer: create the file, then publish, then map it together with the others
+                with open(self._path(f"{numel}_{k}"), "wb") as f:
+                    f.truncate(numel * 4)
+                self.paths.append(self._path(f"{numel}_{k}"))
             self.ctrl[1] = k
             self.ctrl[0] = self.job
         else:
             self._wait(0, self.job, "the master to publish the job")
-            buf = self._map(numel, int(self.ctrl[1]))
+            k = int(self.ctrl[1])
+        buf = self._map(numel, k, touch)
         return buf.view(tuple(shape))
 
     def finish(self):
@@ -515,8 +557,21 @@ def upscale_static_host(host_image: torch.Tensor, denoiser, tile_width: int, til
         job = StaticJob.get(plan, B, device, group, denoiser, None, graphed)
         if not job.sharded:
             return NotImplemented
+        import time as _time
+        timing = stats is not None and bool(stats.get("time_phases"))
+        marks, cpu = [], {}
+
+        def mark(name):                                # GPU-side phase boundaries on this rank's stream
+            if timing:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        t_cpu = _time.perf_counter()
         shared = SharedHost.get(group)
-        out = shared.begin((B, H, W, 3))
+        ya, yb = job.rows[rank]
+        out = shared.begin((B, H, W, 3), touch=(ya * W * 3, yb * W * 3) if B == 1 else None)
+        cpu["begin (host hand-shake: result buffer of this job)"] = (_time.perf_counter() - t_cpu) * 1e3
         y0, y1 = job.rows[rank]
         n = y1 - y0
         max_rows = max(b - a for a, b in job.rows)
@@ -531,31 +586,48 @@ def upscale_static_host(host_image: torch.Tensor, denoiser, tile_width: int, til
                 job.stage = torch.empty((B, max(max_rows, 1), W, 3), dtype=torch.float32, pin_memory=True)
             job.stage[:, :n].copy_(x[:, y0:y1])
             src = None
+        mark("start")
         for b in range(B):                             # H2D of the slab, one contiguous span per frame
             if n > 0:
                 slab[b, :n].copy_(job.stage[b, :n] if src is None else x[b, y0:y1], non_blocking=True)
                 # `slab[b]` holds rows y0..y1 of frame b: hand the kernel the address its row 0 would have
                 nat.quantize_rows(slab[b].data_ptr() - y0 * row_bytes, work[b].data_ptr(), 1, H, W, pitch, y0, y1, _stream_ptr())
+        mark("upload + quantise own slab")
         job.peer.barrier(0)                            # every slab of the quantised input is in its owner's working canvas
-        for q in range(world):                         # all-gather of the u8 slabs: peer loads over NVLink
-            a, b_ = job.rows[q]
-            if q != rank and b_ > a:
-                work[:, a:b_].copy_(job.work.peer_view(q, (B, H, pitch))[:, a:b_], non_blocking=True)
+        mark("barrier (slabs quantised)")
+        live = [q for q in range(world) if job.rows[q][1] > job.rows[q][0]]      # all-gather of the u8 slabs: peer loads over NVLink
+        bounds = [0] + [job.rows[q][1] for q in live]
+        bounds[-1] = H
+        nat.gather_canvas([job.work.ptrs[q] for q in live], bounds, work.data_ptr(), B, H, W, pitch, _stream_ptr())
+        mark("all-gather of the u8 slabs over NVLink")
         job.peer.barrier(1)                            # nobody blends into a working canvas that is still being read
+        mark("barrier (gathered)")
         canvas = job.run_tiles(None, denoiser, resident=True)
+        mark("tiles")
         job.peer.barrier(0)                            # every payload is complete and visible
+        mark("barrier (payloads)")
         fin.launches = fin.algo_bytes = 0
         for b in range(B):
             if n > 0:
                 nat.quantize_rows(slab[b].data_ptr() - y0 * row_bytes, fin.buf[b].data_ptr(), 1, H, W, pitch, y0, y1, _stream_ptr())
         fin.blend(job.final_order, job.peer.buf, job.final_offs, part=(rank, world))
+        mark("composite own slab")
         job.peer.barrier(1)                            # nobody refills a payload that is still being read
+        mark("barrier (composited)")
         for b in range(B):
             if n > 0:
                 nat.dequantize_rows(fin.buf[b].data_ptr(), slab[b].data_ptr() - y0 * row_bytes, 1, H, W, pitch, y0, y1, _stream_ptr())
                 out[b, y0:y1].copy_(slab[b, :n], non_blocking=True)
+        mark("dequantise + download own slab")
+        t_cpu = _time.perf_counter()
         torch.cuda.current_stream(device).synchronize()
+        cpu["stream synchronize"] = (_time.perf_counter() - t_cpu) * 1e3
+        t_cpu = _time.perf_counter()
         shared.finish()
+        cpu["finish (host hand-shake: all slabs landed)"] = (_time.perf_counter() - t_cpu) * 1e3
+        if timing:
+            stats["phase_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+            stats["phase_ms"].update({"cpu: " + k: v for k, v in cpu.items()})
     if stats is not None:
         stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches + fin.launches + 3 * B
         stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes + fin.algo_bytes

@@ -106,7 +106,7 @@ class UltimateSDUpscaleDistributed:
 
         src_device = upscaled_image.device
         dev = src_device if upscaled_image.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        self.last_stats = {}
+        self.last_stats = {"time_phases": True} if getattr(self, "time_phases", False) else {}
         if multi_job_id and is_worker and world == 1:
             # The reference's HTTP orchestrator started this process as a worker (static.py:191-314).  Its tile queue
             # and PNG transport are not part of this package (an SPMD launch, one rank per GPU, replaces them): do what

@@ -233,6 +233,11 @@ int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H
 #define USDU_MAX_SLABS 16
 int usdu_gather_dequantize(const uint8_t* const* slab_canvas_dev, const int32_t* slab_rows, int n_slabs,
                            float* img_dev, int B, int H, int W, int64_t pitch, void* stream);
+/* The all-gather of the quantised INPUT slabs in one launch (host path of a multi-GPU job): rows
+ * [slab_rows[q], slab_rows[q+1]) of canvas_dev are copied from slab_canvas_dev[q]; the slab whose pointer IS canvas_dev
+ * (this rank's own) is skipped.  Replaces every worker holding the whole canvas, upscale/modes/static.py:209-212. */
+int usdu_gather_canvas(const uint8_t* const* slab_canvas_dev, const int32_t* slab_rows, int n_slabs,
+                       uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, void* stream);
 /* Q1 for transport: dst[i] = (uint8)(255.f * src[i]); n elements (worker_comms.py:30-33) */
 int usdu_pack_tiles_u8(const float* src_dev, uint8_t* dst_dev, int64_t n, void* stream);
 /* receiving side of the transport: dst[i] = src[i] / 255.0f (api/job_routes.py:104-132) */
