@@ -79,6 +79,51 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+class NvlinkCounters:
+    """NVLink payload bytes of this rank's GPU (NVML field values NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX summed over the
+    links, KiB): read before and after a timed loop -> bytes per step that crossed the link, measured, not modelled."""
+
+    def __init__(self, index: int):
+        self.h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(index).uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            self.nv = pynvml
+            self.ids = [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF), (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)]
+            self.read()
+        except Exception:
+            self.h = None
+
+    def read(self):
+        if self.h is None:
+            return None
+        try:
+            v = self.nv.nvmlDeviceGetFieldValues(self.h, self.ids)
+            out = []
+            for x in v:
+                if x.nvmlReturn != 0:
+                    return None
+                out.append(int(x.value.ullVal) * 1024)
+            return out                       # [tx bytes, rx bytes]
+        except Exception:
+            return None
+
+
+def kernel_source_hash() -> str:
+    """SHA-256 over the CUDA sources and the C header the library is built from (a stamp that is the same on the build
+    container and on the GPU box; the .so itself is rebuilt per box)."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "comfyui-distributed_b200", "csrc", "*.cu*")) + [os.path.join(ROOT, "include", "usdu_b200.h")]):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -283,6 +328,9 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=3, help="tiles of the bounded cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-t1", action="store_true", help="skip the supplementary SDXL-cost (T1) measurement")
+    ap.add_argument("--semantics", default="static", choices=["static", "exact"],
+                    help="N > 1: the reference's static mode (default, the headline) or the cooperative single-GPU DAG "
+                         "(dist.upscale_exact: bit-identical to N = 1 at any world size; device-resident line only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -329,12 +377,18 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
+    exact = world > 1 and args.semantics == "exact"
+
     def step_device(stats=None):
+        if exact:
+            return udist.upscale_exact(img, den, tile, tile, pad, blur, True, stats=stats)
         if world > 1:
             return udist.upscale_static(img, den, tile, tile, pad, blur, True, stats=stats)
         return engine.upscale_single(img, den, tile, tile, pad, blur, True, stats=stats)
 
     def step_e2e():
+        if exact:                    # the node API has no switch for it: the supplementary line reports the device-resident job only
+            return step_device()
         return node.run(host, model, None, None, None, SEED, 20, 8.0, "euler", "normal", DENOISE, tile, tile, pad, blur,
                         True, False, multi_job_id="bench" if world > 1 else "")[0]
 
@@ -355,7 +409,7 @@ def main():
 
     # ---- parity first: one untimed step per arm; rank 0's result against the committed digest of the reference --------
     parity = {"checked": False, "match": None, "why": "no digest for this workload / sampler"}
-    exp, exp_key = expected_digest(args.workload, world)
+    exp, exp_key = expected_digest(args.workload, 1 if exact else world)
     if args.denoiser == "t0" and exp is not None:
         out_dev, out_e2e = step_device(), step_e2e()
         barrier()
@@ -363,7 +417,7 @@ def main():
         if rank == 0:
             got = {"device_arm": result_digest(out_dev), "e2e_arm": result_digest(out_e2e)}
             plan0 = planner_mod.get_plan(W, H, tile, tile, pad, blur, True)
-            same_asg = world == 1 or [list(map(int, a)) for a in plan0.partition(world)] == exp.get("assignment")
+            same_asg = world == 1 or exact or [list(map(int, a)) for a in plan0.partition(world)] == exp.get("assignment")
             match = same_asg and all(v == exp["sha256"] for v in got.values())
             parity = {"checked": True, "match": bool(match), "source": f"tests/golden/bench_digests.json:{exp_key} ({exp['how']})",
                       "expected": exp["sha256"], **got}
@@ -388,7 +442,21 @@ def main():
     barrier()
     clocks.start()
     stats = {}
+    nvl = NvlinkCounters(local) if world > 1 else None
+    nvl0 = nvl.read() if nvl else None
     ms_step = timed(lambda: step_device(stats), args.steps)
+    nvl1 = nvl.read() if nvl else None
+    nvlink = None
+    if nvl0 is not None and nvl1 is not None:
+        t = torch.tensor([(nvl1[0] - nvl0[0]) / args.steps, (nvl1[1] - nvl0[1]) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        td.all_gather(allr, t)
+        nvlink = {"source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX over the timed device loop, per step",
+                  "tx_MB_per_step_by_rank": [round(float(a[0]) / 1e6, 2) for a in allr],
+                  "rx_MB_per_step_by_rank": [round(float(a[1]) / 1e6, 2) for a in allr]}
+        rx0 = float(allr[0][1])
+        if rx0 > 0:
+            nvlink["master_rx_GBps_if_spread_over_the_step"] = round(rx0 / (ms_step * 1e-3) / 1e9, 1)
     # (the sampler keeps running through the per-kernel and end-to-end timed loops below: K steps of a
     # 1.3 ms job are over before nvidia-smi's first 100 ms tick)
     stats["gpu_launches"] = stats.get("gpu_launches", 0) // args.steps        # per step
@@ -430,6 +498,36 @@ def main():
         engine.PROFILE = None
         kern = prof.summary()
         timing_note = "CUDA events around every launch of one step after the timed region"
+
+    # ---- the two tile kernels in isolation on a machine-filling work list: ALL tiles in one launch (the shape of the
+    # static-mode final composite), CUDA events around each launch; the in-situ numbers above are 31 small launches
+    isolated = None
+    if world == 1:
+        plan_i = planner_mod.get_plan(W, H, tile, tile, pad, blur, True)
+        dp_i = engine.DevicePlan.get(plan_i, dev)
+        cv = engine.Canvas(dp_i, B).load(img)
+        ids_i = list(range(len(plan_i.tiles)))
+        buf_i, offs_i = cv.crop(ids_i)
+        src_i = torch.rand(buf_i.numel(), device=dev)
+
+        def med_us(fn, reps=7):
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(reps):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); fn(); b_.record(); torch.cuda.synchronize()
+                ts.append(a_.elapsed_time(b_) * 1e3)
+            return sorted(ts)[len(ts) // 2]
+
+        cb = dp_i.crop_list(tuple(ids_i), B, cv.path_crop)[0].algo_bytes * B
+        bb = dp_i.blend_list(tuple(ids_i), offs_i, False, cv.path_blend, B)[0].algo_bytes * B
+        t_c = med_us(lambda: cv.crop(ids_i, out=buf_i))
+        t_b = med_us(lambda: cv.blend(ids_i, src_i, offs_i))
+        isolated = {"what": f"all {len(ids_i)} tiles in ONE launch, eager, CUDA events, median of 7 (inputs larger than L2)",
+                    "blend": {"us": round(t_b, 1), "GBps": round(bb / t_b / 1e3, 1), "frac": round(bb / t_b / 1e3 / measured_peak_gbs()[0], 4), "algorithmic_MB": round(bb / 1e6, 1)},
+                    "crop_resize": {"us": round(t_c, 1), "GBps": round(cb / t_c / 1e3, 1), "frac": round(cb / t_c / 1e3 / measured_peak_gbs()[0], 4), "algorithmic_MB": round(cb / 1e6, 1)}}
+        del cv, buf_i, src_i
 
     # ---- N > 1: where the step goes, per phase, max over ranks (CUDA events at the phase boundaries) -----------------
     phases = None
@@ -515,13 +613,27 @@ def main():
     dom = "blend"
     k = kern.get(dom, {"gbps": 0.0, "launches": 0, "avg_us": 0.0, "bytes": 0})
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_blend_traffic.json")
-    if os.path.isfile(tp):
+    tp = os.path.join(ROOT, "profiles", "r02_traffic_cfg2.json")
+    if os.path.isfile(tp) and world == 1 and args.workload == "cfg2_4k_to_8k_sdxl_512px":
         tj = json.load(open(tp))
-        traffic = tj.get("dram_bytes_per_launch")
-        traffic_note = f"ncu --set full, {tj.get('launch')}: {tj.get('duration_us')} us, algorithmic 43.1 MB (profiles/r01_blend_traffic.json)"
-    roofline = {"bound": "hbm", "kernel": "usdu::fast::blend_fast_kernel", "achieved": round(k["gbps"], 1), "peak": peak,
+        if tj.get("source_hash") == kernel_source_hash():
+            traffic = tj["blend"]["dram_bytes_per_launch"]
+            traffic_note = (f"ncu dram__bytes_read+write summed over the {tj['blend']['launches']} blend launches of one step "
+                            f"({tj['blend']['dram_bytes_per_step'] / 1e6:.1f} MB = {tj['blend']['traffic_over_algorithmic']} x algorithmic), "
+                            f"per launch; profiles/r02_traffic_cfg2.json, captured from kernel sources {tj['source_hash']} = the ones running")
+        else:
+            traffic_note = (f"profiles/r02_traffic_cfg2.json was captured from kernel sources {tj.get('source_hash')}, the library here is built "
+                            f"from {kernel_source_hash()}: traffic withheld (re-capture with tools/one_step.py + tools/traffic_summary.py)")
+    plan_r = planner_mod.get_plan(W, H, tile, tile, pad, blur, True)
+    survey_bytes = sum(6 * t.pw * t.ph + 6 * t.ew * t.eh for t in plan_r.tiles) * B      # u8 canvas r+w, fp16 tiles
+    kernel_name = {2: "usdu::mma::blend_mma_kernel (tensor cores: mma.sync.m16n8k32 u8 x 8-bit coefficient limbs)",
+                   1: "usdu::fast::blend_fast_kernel", 0: "usdu::blend_kernel (generic)"}[min(plan_r.kernel_path(None), engine.PATH_BLEND)]
+    step_us = k["avg_us"] * max(k["launches"], 1)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": round(k["gbps"], 1), "peak": peak,
                 "unit": "GB/s", "frac": round(k["gbps"] / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
+                "frac_survey_bytes": round(survey_bytes / (step_us * 1e-6) / 1e9 / peak, 4) if (step_us > 0 and world == 1) else None,
+                "survey_bytes_per_step": survey_bytes,
+                "isolated_full_launch": isolated,
                 "peak_source": peak_src,
                 "launches_per_step": k["launches"], "avg_launch_us": round(k["avg_us"], 2),
                 "algorithmic_bytes_per_step": k["bytes"],
@@ -533,7 +645,9 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "canvas": [B, H, W], "tile": tile, "padding": pad, "mask_blur": blur,
                        "tiles": stats.get("tiles"), "waves": stats.get("waves"), "denoiser": den_name,
-                       "semantics": "exact progressive (single_gpu)" if world == 1 else "static replay, fixed partition",
+                       "semantics": ("exact progressive (single_gpu)" if world == 1 else
+                                     "exact progressive on N ranks (dist.upscale_exact: per-wave all-gather, replicated blend)" if exact
+                                     else "static replay, fixed partition"),
                        "cuda_graph": bool(engine.USE_CUDA_GRAPHS and getattr(den, "cuda_graph_safe", False)),
                        "transport": stats.get("transport"),
                        "l2": "inputs larger than L2 (canvas 99.5 MB u8 + 398 MB fp32 image per step)"},
@@ -551,6 +665,8 @@ def main():
             "roofline": roofline}
     if phases is not None:
         line["phase_ms_max_over_ranks"] = phases
+    if nvlink is not None:
+        line["nvlink"] = nvlink
     if e2e_phases is not None:
         line["e2e"]["phase_ms_max_over_ranks"] = e2e_phases
     if t1_info is not None:

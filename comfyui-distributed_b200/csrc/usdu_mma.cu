@@ -318,13 +318,15 @@ struct CropEpilogue {
     float* dst;          // &out[tile][b][oy0][ox0][0]
     int64_t row_pitch;   // floats per output row
     int ow3, rows_out;
-    const float* lut;
     struct Pre {};
     __device__ __forceinline__ Pre prefetch(int, int, int) const { return Pre{}; }
     __device__ __forceinline__ void store(const Pre&, int, int r, int strip, uint32_t v) {
         if (r >= 0 && r < rows_out && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
+            // u / 255.0f in arithmetic (dequant_u8_fast): a 256-entry table in shared memory costs 4 data-dependent loads per
+            // thread that collide on banks -- 78 % of the kernel's excess shared-memory wavefronts in the r02e profile
             float4 o;
-            o.x = lut[v & 0xFF]; o.y = lut[(v >> 8) & 0xFF]; o.z = lut[(v >> 16) & 0xFF]; o.w = lut[v >> 24];
+            o.x = dequant_u8_fast(v & 0xFF); o.y = dequant_u8_fast((v >> 8) & 0xFF);
+            o.z = dequant_u8_fast((v >> 16) & 0xFF); o.w = dequant_u8_fast(v >> 24);
             __stcs(reinterpret_cast<float4*>(dst + (int64_t)r * row_pitch + 4 * strip), o);
         }
     }
@@ -339,20 +341,18 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int plane_rows, int mid_rows, int W3,
                 const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job] [lut] [bar] [planes]
+    // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job] [bar] [planes]
     constexpr bool kTma = kSrc == 1;
     const size_t region = kTma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
     uint32_t* mid = reinterpret_cast<uint32_t*>(smem);
     uint8_t* raw = smem;
     int32_t* job_sm = reinterpret_cast<int32_t*>(smem + region);
-    float* lut = reinterpret_cast<float*>(smem + region + kHeadBytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + region + kHeadBytes + 1024);
-    uint8_t* planes = smem + region + kHeadBytes + 1024 + 16;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + region + kHeadBytes);
+    uint8_t* planes = smem + region + kHeadBytes + 16;
     const int PB = plane_pitch(patch_w);
     pdl_launch_dependents();
     load_job(job_sm, jobs, blockIdx.x);
     if (kTma && threadIdx.x == 0) tma::mbar_init(bar, 1);
-    for (int i = threadIdx.x; i < 256; i += kT) lut[i] = dequant_u8_fast(i);
     __syncthreads();
     const JobView J{job_sm};
     const int b = blockIdx.y;
@@ -382,7 +382,6 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
               (int64_t)J[USDU_J_DST_X] * 3;
     epi.ow3 = J[USDU_J_COLS_OUT] * 3;
     epi.rows_out = J[USDU_J_ROWS_OUT];
-    epi.lut = lut;
     both_passes<KSMAX>(planes, mid, tabs, J, PB, plane_rows, J[USDU_J_CY1], epi);
 }
 
@@ -524,7 +523,7 @@ blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ m
 
 static size_t crop_smem(int patch_w, int plane_rows, int mid_rows, bool use_tma) {
     const size_t region = use_tma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
-    return region + kHeadBytes + 1024 + 16 + planes_bytes(patch_w, plane_rows);
+    return region + kHeadBytes + 16 + planes_bytes(patch_w, plane_rows);
 }
 static size_t blend_smem(int patch_w, int plane_rows, int mid_rows, int block_rows) {
     return (size_t)2 * block_rows * kDBox + kHeadBytes + 16 + planes_bytes(patch_w, plane_rows) + mid_bytes(mid_rows);

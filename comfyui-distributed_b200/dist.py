@@ -651,17 +651,50 @@ def _payload_buffer(nbytes: int, device) -> torch.Tensor:
     return _PAYLOADS[key]
 
 
+class ExactJob:
+    """Per-geometry state of `semantics="exact"` jobs: for every dependency wave the round-robin shares, the payload
+    layout, the send buffer and the gathered buffer (all sizes follow from the plan: no size exchange, no host sync,
+    nothing allocated per job)."""
+
+    _cache: Dict[tuple, "ExactJob"] = {}
+
+    def __init__(self, plan, B: int, device, group):
+        from .engine import _sorted_by_shape
+        self.plan, self.B = plan, B
+        rank, world = dist_info(group)
+        self.waves = []
+        for wave in plan.waves():
+            wave = _sorted_by_shape(plan, wave)
+            shares = [wave[r::world] for r in range(world)]
+            where, sizes = tile_payload_layout(plan, shares, B)
+            cap = (max(max(sizes), 16) + 15) // 16 * 16
+            offs_all = np.array([where[t][0] * cap + where[t][1] for t in wave], dtype=np.int64)
+            send = torch.zeros(cap, dtype=torch.uint8, device=device)
+            recv = torch.empty(world * cap, dtype=torch.uint8, device=device) if world > 1 else send
+            self.waves.append((wave, shares[rank], where, offs_all, send, recv))
+
+    @classmethod
+    def get(cls, plan, B, device, group) -> "ExactJob":
+        key = (id(plan), B, str(device), id(group))
+        job = cls._cache.get(key)
+        if job is None or job.plan is not plan:
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            job = cls._cache[key] = ExactJob(plan, B, device, group)
+        return job
+
+
 def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int, mask_blur: int,
                   force_uniform_tiles: bool = True, group=None, stats: Optional[dict] = None) -> torch.Tensor:
     """`semantics="exact"`: N ranks cooperatively execute the SINGLE-GPU
     progressive job, so the result is bit-identical to process_single_gpu at any world size
     (the reference's static mode is not -- SURVEY.md 8c).  Every rank keeps a full canvas;
     the tiles of each dependency wave are split round-robin, each rank crops + samples its
-    share, one all-gather per wave exchanges the truncated u8 tiles, and every rank blends
-    the whole wave (replicated blend keeps all canvases identical).  Every rank returns the
-    result."""
+    share and packs the truncated u8 tiles straight into its send buffer, one all_gather_into_tensor
+    per wave exchanges them, and every rank blends the whole wave (replicated blend keeps all canvases
+    identical).  Every rank returns the result."""
     from . import _native as nat
-    from .engine import Canvas, DevicePlan, _require_cuda, _stream_ptr, denoise_packed, _sorted_by_shape
+    from .engine import Canvas, DevicePlan, _require_cuda, _stream_ptr, denoise_packed
     from .planner import get_plan
 
     _require_cuda(image, "image")
@@ -670,34 +703,31 @@ def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: i
     plan = get_plan(W, H, tile_width, tile_height, padding, mask_blur, force_uniform_tiles)
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
-        canvas = Canvas(dp, B).load(image)
-        n_waves = 0
-        for wave in plan.waves():
-            wave = _sorted_by_shape(plan, wave)
-            shares = [wave[r::world] for r in range(world)]
-            mine = shares[rank]
-            where, sizes = tile_payload_layout(plan, shares, B)
-            payload = torch.zeros(max(sizes[rank], 16), dtype=torch.uint8, device=image.device)
+        job = ExactJob.get(plan, B, image.device, group)
+        canvas = Canvas(dp, B).load(image.contiguous())
+        for wave, mine, where, offs_all, send, recv in job.waves:
             if mine:
                 buf, offs = canvas.crop(mine)
                 out = denoise_packed(plan, mine, buf, offs, B, denoiser)
-                q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
-                nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
+                sizes = [B * plan.tiles[t].ph * plan.tiles[t].pw * 3 for t in mine]
+                base = where[mine[0]][1]
+                if all(sz % 16 == 0 for sz in sizes) and all(where[t][1] == base + int(offs[i]) for i, t in enumerate(mine)):
+                    nat.pack_tiles_u8(out.data_ptr(), send[base:].data_ptr(), out.numel(), _stream_ptr())     # one dense span
+                else:
+                    q = torch.empty(out.numel(), dtype=torch.uint8, device=out.device)
+                    nat.pack_tiles_u8(out.data_ptr(), q.data_ptr(), out.numel(), _stream_ptr())
+                    for i, tid in enumerate(mine):
+                        send[where[tid][1]: where[tid][1] + sizes[i]] = q[int(offs[i]): int(offs[i]) + sizes[i]]
                 canvas.launches += 1
-                for i, tid in enumerate(mine):
-                    t = plan.tiles[tid]
-                    n = B * t.ph * t.pw * 3
-                    payload[where[tid][1]: where[tid][1] + n] = q[int(offs[i]): int(offs[i]) + n]
-            gathered, _ = all_gather_bytes(payload, group)
-            cap = gathered.shape[1]
-            offs_all = np.array([where[t][0] * cap + where[t][1] for t in wave], dtype=np.int64)
-            canvas.blend(wave, gathered.view(-1), offs_all)
-            n_waves += 1
+            if world > 1:
+                td.all_gather_into_tensor(recv, send, group=group)
+            canvas.blend(wave, recv, offs_all)
         res = canvas.result()
     if stats is not None:
         stats["gpu_launches"] = stats.get("gpu_launches", 0) + canvas.launches
         stats["algo_bytes"] = stats.get("algo_bytes", 0) + canvas.algo_bytes
-        stats["tiles"], stats["waves"] = len(plan.tiles), n_waves
+        stats["tiles"], stats["waves"] = len(plan.tiles), len(job.waves)
+        stats["transport"] = "single" if world == 1 else "nccl all_gather_into_tensor per wave (sizes from the plan)"
     return res
 
 
@@ -722,6 +752,36 @@ def collector_order(world: int, enabled_worker_ids: Sequence[str], worker_id_of_
         if w not in seen:
             order.append(rank_of[w])
     return order
+
+
+def gather_to_root(payload: torch.Tensor, extra: dict, group=None):
+    """Collector transport: ONLY rank 0 consumes the batches, so the u8 images travel to rank 0 and nowhere else -- one
+    gather_object of the small per-rank records ({"shape": ..., **extra}: worker id, audio) and one receive per worker
+    with its exact size (nodes/collector.py:84-119 + api/job_routes.py:273-343 POST every image to the master).
+    -> (u8 tensors [B_r, H, W, C] by rank, records by rank) on rank 0, (None, None) elsewhere."""
+    rank, world = dist_info(group)
+    record = {"shape": [int(v) for v in payload.shape], **extra}
+    if world == 1:
+        return [payload], [record]
+    root = td.get_global_rank(group, 0) if group is not None else 0
+    records = [None] * world if rank == 0 else None
+    td.gather_object(record, records, dst=root, group=group)
+    flat = payload.contiguous().view(-1)
+    if rank != 0:
+        if flat.numel():
+            td.send(flat, dst=root, group=group)
+        return None, None
+    parts, reqs = [payload], []
+    for r in range(1, world):
+        shape = records[r]["shape"]
+        buf = torch.empty(int(np.prod(shape)), dtype=torch.uint8, device=payload.device)
+        if buf.numel():
+            src = td.get_global_rank(group, r) if group is not None else r
+            reqs.append(td.irecv(buf, src=src, group=group))
+        parts.append(buf.view(shape))
+    for q in reqs:
+        q.wait()
+    return parts, records
 
 
 def gather_image_payloads(payload: torch.Tensor, shape: Sequence[int], group=None):

@@ -40,19 +40,16 @@ def _native_unpack(q: torch.Tensor) -> torch.Tensor:
 
 
 def collect_images(images: torch.Tensor, enabled_worker_ids, worker_id: str, delegate_only: bool = False,
-                   group=None, pack=_native_pack, unpack=_native_unpack):
-    """SPMD collective behind the node.  Returns (combined CPU batch, rank order) on
-    rank 0 and (None, None) on the other ranks."""
+                   group=None, pack=_native_pack, unpack=_native_unpack, audio=None):
+    """SPMD collective behind the node: the u8 batches and the small per-rank records (worker id, audio) travel to
+    rank 0 only (dist.gather_to_root).  Returns (combined CPU batch, rank order, audio pieces by rank) on rank 0 and
+    (None, None, None) on the other ranks."""
     rank, world = usdu_dist.dist_info(group)
     q = pack(images)
-    parts = usdu_dist.gather_image_payloads(q, list(q.shape), group)
-    ids = [None] * world
-    if world > 1:
-        td.all_gather_object(ids, str(worker_id), group=group)
-    else:
-        ids = [str(worker_id)]
+    parts, records = usdu_dist.gather_to_root(q, {"worker_id": str(worker_id), "audio": audio}, group)
     if rank != 0:
-        return None, None
+        return None, None, None
+    ids = [rec["worker_id"] for rec in records]
     order = usdu_dist.collector_order(world, enabled_worker_ids, ids)
     out = []
     for r in order:
@@ -63,7 +60,7 @@ def collect_images(images: torch.Tensor, enabled_worker_ids, worker_id: str, del
             out.append(unpack(parts[r]).cpu())
     if not out:
         raise ValueError("No image data collected from master or workers")
-    return torch.cat(out, dim=0).contiguous(), order
+    return torch.cat(out, dim=0).contiguous(), order, [rec["audio"] for rec in records]
 
 
 def combine_audio(pieces, empty_audio):
@@ -124,13 +121,18 @@ class DistributedCollectorNode:
         rank, world = usdu_dist.dist_info()
         enabled = [str(w) for w in json.loads(enabled_worker_ids)]
         if world == 1:  # no participants besides the master (collector.py:255-256)
+            if is_worker:
+                # started as an HTTP worker of the reference's orchestrator: there is no torch.distributed peer to send the
+                # batch to, and the reference's HTTP collection is not part of this package -- say so instead of dropping it
+                import warnings
+                warnings.warn("DistributedCollector (B200): running as an HTTP worker of the reference's orchestrator is not "
+                              "supported (launch one rank per GPU with torch.distributed); this worker's images stay local.",
+                              RuntimeWarning, stacklevel=2)
             return (images, audio if audio is not None else empty_audio)
         wid = worker_id if (worker_id or rank == 0) else f"rank{rank}"
         if not enabled:  # SPMD launch without the reference's orchestrator: every rank is enabled
             enabled = [f"rank{r}" for r in range(1, world)]
-        combined, order = collect_images(images, enabled, wid, delegate_only=delegate_only)
-        audios = [None] * world
-        td.all_gather_object(audios, audio)
+        combined, order, audios = collect_images(images, enabled, wid, delegate_only=delegate_only, audio=audio)
         if rank != 0:
             return (images, audio if audio is not None else self.EMPTY_AUDIO)
         pieces = [audios[r] for r in order if not (r == 0 and delegate_only)]

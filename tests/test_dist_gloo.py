@@ -112,7 +112,7 @@ def _unpack_cpu(q):
 def _w_collect(rank, world):
     g = torch.Generator().manual_seed(100 + rank)
     images = torch.rand(1 + rank, 6, 5, 3, generator=g)  # different batch sizes per rank
-    combined, order = collect_images(images, ["w1"], "" if rank == 0 else "w1", pack=_pack_cpu, unpack=_unpack_cpu)
+    combined, order, _ = collect_images(images, ["w1"], "" if rank == 0 else "w1", pack=_pack_cpu, unpack=_unpack_cpu)
     if rank != 0:
         assert combined is None
         return
@@ -129,7 +129,7 @@ def test_collector_two_ranks():
 
 def _w_delegate(rank, world):
     images = torch.full((1, 4, 4, 3), 0.1 * (rank + 1))
-    combined, order = collect_images(images, ["w1"], "" if rank == 0 else "w1", delegate_only=True, pack=_pack_cpu,
+    combined, order, _ = collect_images(images, ["w1"], "" if rank == 0 else "w1", delegate_only=True, pack=_pack_cpu,
                                      unpack=_unpack_cpu)
     if rank == 0:
         assert combined.shape[0] == 1                    # master excluded (collector.py:270-274)

@@ -24,8 +24,17 @@ pytestmark = pytest.mark.gpu
 DIGESTS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sweep_ref_digests.json")))["digests"]
 
 
+@pytest.fixture(params=["tensor-core", "integer-pipe"])
+def kernels(request):
+    """Default kernel choice (tensor-core where the plan allows, else the integer-pipe fast ones, else generic) and the
+    same sweep with the tensor-core kernels switched off."""
+    engine.FORCE_NO_MMA = request.param == "integer-pipe"
+    yield request.param
+    engine.FORCE_NO_MMA = False
+
+
 @pytest.mark.parametrize("case", sweep_cases(), ids=lambda c: f"{c[0]}-{c[1]}-b{c[2]}-{c[4]}x{c[3]}-t{c[5]}x{c[6]}-p{c[7]}-m{c[8]}-{'u' if c[9] else 'n'}")
-def test_whole_job_matches_oracle_and_reference(case):
+def test_whole_job_matches_oracle_and_reference(case, kernels):
     i, kind, B, H, W, tw, th, pad, blur, uniform = case
     img = make_input(kind, i, B, H, W)
     seed, den = sweep_sampler(i)
