@@ -71,7 +71,12 @@ def crop_control_hints(opts: dict, region: Region, canvas_size, tile_size):
     c = opts.get("control")
     if c is None:
         return
-    head = copy.copy(c)
+    def _copy(ctrl):
+        # ControlNet.copy() is what the reference calls (utils/usdu_utils.py:297-312): it creates a fresh control object
+        # WITHOUT the cached cond_hint / timestep state a shallow copy would carry over; copy.copy is for test doubles
+        return ctrl.copy() if callable(getattr(ctrl, "copy", None)) else copy.copy(ctrl)
+
+    head = _copy(c)
     opts["control"] = head
     node = head
     while node is not None:
@@ -80,7 +85,7 @@ def crop_control_hints(opts: dict, region: Region, canvas_size, tile_size):
         hint = hint[:, :, hy1:hy2, hx1:hx2]
         node.cond_hint_original = F.interpolate(hint, size=(tile_size[1], tile_size[0]), mode="nearest-exact")
         prev = getattr(node, "previous_controlnet", None)
-        prev = copy.copy(prev) if prev is not None else None
+        prev = _copy(prev) if prev is not None else None
         if hasattr(node, "set_previous_controlnet"):
             node.set_previous_controlnet(prev)
         else:

@@ -25,7 +25,8 @@ def test_reference_arm_single_process():
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["higher_is_better"] is True and d["gpu_launches"] == 0
     assert d["value"] > 0 and abs(d["ms_per_step"] - 0.262144 / d["value"] * 1e3) < 1e-6
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
+    # the reference's own code when oracle/_ref (or /root/reference) is there, the cost-faithful port otherwise
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "cfg1_512_256px"
 
@@ -39,4 +40,4 @@ def test_reference_arm_http_workers():
     lines = _run("--gpus", "2", "--steps", "1", "--warmup", "0")
     d = json.loads(lines[-1])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
-    assert "HTTP" in json.dumps(d["cpu_baseline"])
+    assert "aiohttp" in json.dumps(d["cpu_baseline"]) or "HTTP" in json.dumps(d["cpu_baseline"])

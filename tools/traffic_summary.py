@@ -30,7 +30,10 @@ def to_us(v):
     return val * {"ns": 1e-3, "us": 1, "ms": 1e3, "usecond": 1, "nsecond": 1e-3, "msecond": 1e3}.get(unit, 1)
 
 
-from comfyui_distributed_b200 import planner  # noqa: E402  (bench put the package on the path)
+from __graft_entry__ import load_package  # noqa: E402
+
+load_package()
+from comfyui_distributed_b200 import planner  # noqa: E402
 
 B, H, W, tile, pad, blur = bench.WORKLOADS[workload]
 plan = planner.get_plan(W, H, tile, tile, pad, blur, True)
