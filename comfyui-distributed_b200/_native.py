@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libusdu_b200.so")
 
 # constants mirrored from include/usdu_b200.h (checked against the header in tests)
-ABI_VERSION = 7
+ABI_VERSION = 8
 TILE_WORDS = 24
 T_X1, T_Y1, T_EW, T_EH, T_PW, T_PH, T_MASK_OFF, T_MASK_PITCH = range(8)
 T_TAB_CROP_H, T_TAB_CROP_V, T_TAB_BLEND_H, T_TAB_BLEND_V = 8, 9, 10, 11
@@ -42,6 +42,7 @@ JOB_WORDS = 32
 (J_SRC_A, J_SRC_B, J_LEAD, J_COLS, J_ROWS, J_IX0, J_IY0, J_ROWS_H, J_OX_BASE, J_N_OUT_H, J_ROWS_V, J_OY_BASE, J_N_OUT_V,
  J_DST_X, J_DST_Y, J_OFF_LO, J_OFF_HI, J_ROWS_OUT, J_COLS_OUT, J_CX0, J_CX1, J_CY0, J_CY1, J_FLAGS, J_MPITCH, J_PITCH,
  J_FRAME_LO, J_FRAME_HI, J_NEXT, J_TAPS_H, J_TAPS_V) = range(31)
+J_SLOT = 31
 
 
 class NativeError(RuntimeError):
@@ -67,6 +68,8 @@ _SIGNATURES = {
     "usdu_quantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_dequantize_canvas": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_gather_dequantize": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "usdu_level_blend_crop": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "usdu_gather_canvas": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "usdu_tile_crop_resize_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "usdu_quantize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
@@ -198,6 +201,13 @@ def gather_dequantize(slab_ptrs, slab_rows, img_ptr, B, H, W, pitch, stream):
     ptrs = (ctypes.c_void_p * n)(*[int(p) for p in slab_ptrs])
     rows = (c_int32 * (n + 1))(*[int(r) for r in slab_rows])
     _check(lib().usdu_gather_dequantize(ptrs, rows, n, img_ptr, B, H, W, pitch, stream), "usdu_gather_dequantize")
+
+
+def level_blend_crop(canvas_ptr, B, H, W, pitch, tabs_ptr, mask_ptr, bjobs_ptr, n_bheads, b_patch_w, b_patch_h, src_ptr, block_rows,
+                     cjobs_ptr, n_cjobs, c_patch_w, c_patch_h, out_ptr, expect_ptr, n_slots, sync_ptr, flags, stream):
+    _check(lib().usdu_level_blend_crop(canvas_ptr, B, H, W, pitch, tabs_ptr, mask_ptr, bjobs_ptr, n_bheads, b_patch_w, b_patch_h, src_ptr,
+                                       block_rows, cjobs_ptr, n_cjobs, c_patch_w, c_patch_h, out_ptr, expect_ptr, n_slots, sync_ptr,
+                                       flags, stream), "usdu_level_blend_crop")
 
 
 def gather_canvas(slab_ptrs, slab_rows, canvas_ptr, B, H, W, pitch, stream):

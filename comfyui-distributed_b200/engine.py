@@ -74,6 +74,11 @@ PATH_FLAGS = (0, nat.FLAG_FAST, nat.FLAG_MMA)
 _PATHS = {"generic": 0, "fast": 1, "mma": 2}
 PATH_CROP = _PATHS[os.environ.get("USDU_CROP_PATH", "mma")]      # best build per kernel (upper bound: the plan may not support it)
 PATH_BLEND = _PATHS[os.environ.get("USDU_BLEND_PATH", "mma")]
+# blend(k) and crop(k+1) in ONE launch with device-side ready counters (usdu_level_blend_crop).  Correct (full-size digests,
+# 114 GPU tests) but SLOWER on B200 with a T0-cost sampler -- cfg2: 1.530 vs 1.337 ms (profiles/r02l_bench_fused_levels.json):
+# a crop of wave k+1 needs whole TILES of wave k, whose blocks finish late in the grid, so little overlaps, while every blend
+# CTA now waits for its bulk store to COMPLETE and the grid runs at the larger of the two shared-memory footprints.  Off by default.
+FUSE_LEVELS = os.environ.get("USDU_FUSE_LEVELS", "0") == "1"
 USE_CUDA_GRAPHS = True    # capture the wave loop when the sampler is cuda_graph_safe
 
 
@@ -132,6 +137,18 @@ class DevicePlan:
         return self._wl[key]
 
 
+    def level_list(self, blend_ids: Tuple[int, ...], offs: np.ndarray, crop_ids: Tuple[int, ...], B: int, share: int = 1):
+        key = ("level", blend_ids, tuple(int(o) for o in offs), crop_ids, B, share)
+        if key not in self._wl:
+            r = self.plan.level_worklist(blend_ids, offs, crop_ids, B, share)
+            if r is not None:
+                bl, cr, coffs, ctotal, expect = r
+                r = (bl, cr, coffs, ctotal, torch.from_numpy(bl.items).to(self.device), torch.from_numpy(cr.items).to(self.device),
+                     torch.from_numpy(expect).to(self.device))
+            self._wl[key] = r
+        return self._wl[key]
+
+
 class Canvas:
     """The progressive u8 canvas [B, H, pitch] of one participant."""
 
@@ -152,7 +169,8 @@ class Canvas:
         # integer-pipe build otherwise; both give identical bytes
         self.path_crop = min(self.path, PATH_CROP)
         self.path_blend = min(self.path, PATH_BLEND)
-        self.share = 1                      # launches expected to run side by side (tile-granular schedule)
+        self.share = 1
+        self._sync = None                   # ticket + per-tile counters of the fused level launches (left at zero by the kernel)                      # launches expected to run side by side (tile-granular schedule)
 
     @staticmethod
     def pitch_of(W: int) -> int:
@@ -264,6 +282,37 @@ class Canvas:
         self.algo_bytes += wl.algo_bytes * self.B
 
 
+def _canvas_blend_crop(self, blend_ids: Sequence[int], src: torch.Tensor, offs: np.ndarray, crop_ids: Sequence[int]):
+    """ONE launch: composite the processed tiles `blend_ids` (fp32 sampler output `src`) AND crop the tiles `crop_ids` of
+    the next dependency wave, ordered on the device tile by tile (usdu_level_blend_crop).  -> (crop buffer, crop offsets)
+    or None when the launch does not qualify (the caller then issues the two launches)."""
+    if not (FUSE_LEVELS and self.path_crop == 2 and self.path_blend == 2 and src.dtype == torch.float32):
+        return None
+    blend_ids, crop_ids = tuple(int(t) for t in blend_ids), tuple(int(t) for t in crop_ids)
+    r = self.dp.level_list(blend_ids, offs, crop_ids, self.B, self.share)
+    if r is None:
+        return None
+    bl, cr, coffs, ctotal, bitems, citems, expect = r
+    need = 3 + len(blend_ids) * self.B
+    if self._sync is None or self._sync.numel() < need:
+        self._sync = torch.zeros(max(need, 64), dtype=torch.int32, device=self.buf.device)
+    out = torch.empty(ctotal, dtype=torch.float32, device=self.buf.device)
+    p = self.plan
+    src = src.contiguous()
+    flags = nat.FLAG_MMA | (nat.FLAG_MMA_KS2 if (bl.ks2 or cr.ks2) else 0)
+    _launch("level(blend+crop)", (bl.algo_bytes + cr.algo_bytes) * self.B,
+            lambda: nat.level_blend_crop(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch, self.dp.tabs.data_ptr(),
+                                         self.dp.mask_pool.data_ptr(), bitems.data_ptr(), bl.n_launch, bl.patch_w, bl.patch_h,
+                                         src.data_ptr(), bl.block_rows, citems.data_ptr(), citems.shape[0], cr.patch_w, cr.patch_h,
+                                         out.data_ptr(), expect.data_ptr(), len(blend_ids), self._sync.data_ptr(), flags, _stream_ptr()))
+    self.launches += 1
+    self.algo_bytes += (bl.algo_bytes + cr.algo_bytes) * self.B
+    return out, coffs
+
+
+Canvas.blend_crop = _canvas_blend_crop
+
+
 def tile_views(plan: Plan, tile_ids: Sequence[int], buf: torch.Tensor, offs: np.ndarray, B: int):
     """Group consecutive same-shape tiles of a packed buffer into [n, B, ph, pw, 3] views."""
     groups = []
@@ -324,9 +373,13 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     plan, B = canvas.plan, canvas.B
     shipped: Dict[int, torch.Tensor] = {}
     scratch = None
-    for wave in plan.waves(order):
-        wave = _sorted_by_shape(plan, wave)
-        if "crop" in skip and crop_buf is not None:    # the caller cropped this (single) wave itself: GraphedWaves.replay_from_image
+    waves = [_sorted_by_shape(plan, w) for w in plan.waves(order)]
+    fused = None                                   # (crop buffer, offsets) of this wave when the previous level launch made it
+    for k, wave in enumerate(waves):
+        if fused is not None:
+            buf, offs = fused
+            fused = None
+        elif "crop" in skip and crop_buf is not None:    # the caller cropped this (single) wave itself: GraphedWaves.replay_from_image
             offs, total = plan.slot_offsets(wave, B)
             buf = crop_buf[:total]
         elif "crop" in skip:    # bench.py's differencing measurement: same graph minus one kernel kind
@@ -338,7 +391,10 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
             buf, offs = canvas.crop(wave)
         out = denoise_packed(plan, wave, buf, offs, B, denoiser)
         if "blend" not in skip:
-            canvas.blend(wave, out, offs)
+            if not skip and k + 1 < len(waves):    # blend(k) U crop(k+1) as one launch, ordered on the device
+                fused = canvas.blend_crop(wave, out, offs, waves[k + 1])
+            if fused is None:
+                canvas.blend(wave, out, offs)
         if payload is not None:
             sizes = [B * plan.tiles[t].ph * plan.tiles[t].pw * 3 for t in wave]
             base = where[wave[0]][1]
@@ -490,7 +546,7 @@ class GraphedWaves:
             canvas_buf: Optional[torch.Tensor] = None, external_crop: bool = False) -> "GraphedWaves":
         pkey = None if payload is None else (payload.data_ptr(), payload.numel())
         ckey = None if canvas_buf is None else canvas_buf.data_ptr()
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE,
+        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE, FUSE_LEVELS,
                None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey, external_crop)
         gw = cls._cache.get(key)
         if gw is None or gw.canvas.dp is not dp:

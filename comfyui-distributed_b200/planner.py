@@ -600,6 +600,42 @@ class Plan:
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes,
                         block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw, path=path, ks2=ks2), offs, total
 
+    MAX_LEVEL_DEPS = 4
+
+    def level_worklist(self, blend_ids: Sequence[int], offs: np.ndarray, crop_ids: Sequence[int], B: int, share: int = 1):
+        """Work lists of ONE launch that blends wave k (`blend_ids`, sampler output at element offsets `offs`) and crops
+        wave k+1 (`crop_ids`) with device-side ordering (usdu_level_blend_crop).  -> (blend WorkList, crop WorkList, crop
+        offsets, crop total elements, expect int32[n_slots]) or None when the plan / the launch does not qualify
+        (tensor-core records on both sides, crop patch inside the TMA boxes, at most MAX_LEVEL_DEPS dependencies per tile).
+        A crop tile depends on the tiles of `blend_ids` whose windows intersect its own (single_gpu.py:40-64: only
+        overlapping tiles are ordered); slots = positions in blend_ids."""
+        if self.kernel_path(None) != 2 or not blend_ids or not crop_ids:
+            return None
+        bl = self.blend_worklist(blend_ids, offs, 4, 2, B, None, share)
+        cr, coffs, ctotal = self.crop_worklist(crop_ids, B, 2, share)
+        if bl.path != 2 or cr.path != 2 or bl.n_launch <= 0 or (cr.patch_h & 0xFFFF) > 48 or 12 + cr.patch_w * 3 > 512:
+            return None
+        slot_of = {int(t): s for s, t in enumerate(blend_ids)}
+        J = cr.items.reshape(-1, nat.JOB_WORDS).copy()
+        dep_words = (nat.J_CX0, nat.J_CX1, nat.J_CY0, nat.J_FLAGS)
+        J[:, dep_words] = -1
+        tile_of_job = {}
+        row = 0
+        for tid in crop_ids:                       # crop records are laid out tile by tile, blocks row-major
+            t = self.tiles[tid]
+            n = len(range(0, t.pw, nat.FAST_BLOCK_W)) * len(range(0, t.ph, int(J[row, nat.J_CY1])))
+            deps = sorted(slot_of[n_] for n_ in self.neighbors[tid] if n_ in slot_of)
+            if len(deps) > self.MAX_LEVEL_DEPS:
+                return None
+            for d, w in zip(deps, dep_words):
+                J[row:row + n, w] = d
+            row += n
+        assert row == J.shape[0]
+        jb = bl.items.reshape(-1, nat.JOB_WORDS)
+        expect = np.bincount(jb[:, nat.J_SLOT], minlength=len(blend_ids)).astype(np.int32)
+        cr.items = np.ascontiguousarray(J)
+        return bl, cr, coffs, ctotal, expect
+
     # ---- tensor-core job records ---------------------------------------------------------
     def _mma_axis(self, key: Tuple[int, int], base: np.ndarray, extent: np.ndarray):
         """One axis of the tensor-core job records.  base = output index of block column / row 0 (any alignment, may be
@@ -758,7 +794,7 @@ class Plan:
         items[:, 2] = first
         items[:, 3] = counts
         if use_fast:
-            jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh, path == 2)
+            jobs = self._blend_jobs(keys, tids, np.asarray(offs, dtype=np.int64)[seq], first, nbx, bw, bh, path == 2, seq)
             if path == 2:
                 jobs, pw_max, ph_max = jobs
             ks2 = bool(path == 2 and (jobs[:, [nat.J_TAPS_H, nat.J_TAPS_V]] > 1).any())
@@ -772,7 +808,7 @@ class Plan:
                         block_rows=bh, block_cols=bw, rows=rows)
 
 
-    def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh, mma: bool = False):
+    def _blend_jobs(self, keys, tids, src_off, first, nbx, bw, bh, mma: bool = False, seq=None):
         """(block, tile) pairs sorted by (block, blend order) -> fast job records; the first
         record of every block comes first (they form the grid), the rest is chained by NEXT.
         mma: tensor-core flavour of the records (-> records, patch_w, patch_h word)."""
@@ -837,6 +873,8 @@ class Plan:
         same = np.r_[keys[1:] == keys[:-1], False]
         nxt[same] = pos[1:][same[:-1]]
         J[:, nat.J_NEXT] = nxt
+        if seq is not None:
+            J[:, nat.J_SLOT] = seq                  # position of the record's tile in the launch's tile list
         out = np.zeros_like(J)
         out[pos] = J
         if mma:

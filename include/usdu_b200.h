@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define USDU_ABI_VERSION 7
+#define USDU_ABI_VERSION 8
 
 typedef enum usdu_status {
     USDU_OK = 0,
@@ -133,6 +133,7 @@ typedef enum usdu_status {
 #define USDU_J_FRAME_LO 26 /* elements per frame PH*PW*3 */
 #define USDU_J_FRAME_HI 27
 #define USDU_J_NEXT 28     /* blend: index of the next record of the same block, -1 = last */
+#define USDU_J_SLOT 31     /* blend: position of the record's tile in the launch's tile list (usdu_level_blend_crop counts per tile) */
 #define USDU_J_TAPS_H 29   /* taps of the horizontal / vertical axis: 1..USDU_FAST_TAPS (packed rows of 8 int32; a value
                               <= 6 lets the kernel skip the unused last slot) or USDU_FAST_TAPS_WIDE (rows of 16) */
 #define USDU_J_TAPS_V 30
@@ -285,6 +286,21 @@ int usdu_tile_blend(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch,
                     const uint8_t* mask_pool_dev, const int32_t* items_dev, int n_items,
                     const int32_t* cover_dev, int patch_w, int patch_h, const void* src_dev,
                     int src_is_u8, int flags, void* stream);
+
+/* One launch per dependency level of the progressive job: the seam blend of wave k (bjobs: tensor-core blend records,
+ * fp32 source = the sampler's output) AND the crop of wave k+1 (cjobs: tensor-core crop records) in one grid, ordered by
+ * device-side ready counters instead of a kernel boundary: a crop block starts as soon as the tiles of wave k whose
+ * windows touch its tile have been composited (its job words CX0, CX1, CY0, FLAGS = slots of those tiles in the blend
+ * launch's tile list, -1 = none; expect_dev[slot] = canvas blocks that blend the tile).  sync_dev: 3 + n_slots * B
+ * int32, zero before the first use (the kernel leaves it zero; word 2 is an error flag raised when a wait gives up).
+ * Same results as usdu_tile_blend followed by usdu_tile_crop_resize (upscale/modes/single_gpu.py:40-64 only orders
+ * OVERLAPPING tiles).  Tensor-core records only; the crop patch must fit the TMA boxes (USDU_ERR_UNSUPPORTED otherwise:
+ * use the two separate launches). */
+int usdu_level_blend_crop(uint8_t* canvas_dev, int B, int H, int W, int64_t pitch, const int32_t* tabs_dev,
+                          const uint8_t* mask_pool_dev, const int32_t* bjobs_dev, int n_bheads, int b_patch_w,
+                          int b_patch_h, const float* src_dev, int block_rows, const int32_t* cjobs_dev,
+                          int n_cjobs, int c_patch_w, int c_patch_h, float* out_dev,
+                          const int32_t* expect_dev, int n_slots, int32_t* sync_dev, int flags, void* stream);
 
 /* ---- one-channel u8 planes: per-tile conditioning masks (utils/usdu_utils.py:415-442) ---------
  * Window of a separable 8bpc resize of n planes src[n][src_h][src_w] (Image.resize semantics:

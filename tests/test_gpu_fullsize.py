@@ -69,3 +69,20 @@ def test_node_api_on_a_host_tensor_matches_the_reference_digest(name):
                           True, False)
         assert not out.is_cuda and _digest(out) == want
         del out
+
+
+def test_fused_level_launches_give_the_same_canvas():
+    """engine.FUSE_LEVELS: blend(k) U crop(k+1) as one launch ordered by device-side ready counters
+    (usdu_level_blend_crop) -- off by default (measured slower), kept correct: same digest as the reference on cfg2."""
+    B, H, W, tile, pad, blur = WORKLOADS["cfg2_4k_to_8k_sdxl_512px"]
+    want = _expected("cfg2_4k_to_8k_sdxl_512px")
+    img = _canvas(B, H, W).cuda()
+    engine.FUSE_LEVELS = True
+    try:
+        for _ in range(3):                   # eager warm-up inside the capture, then replays: the counters must return to zero
+            out = engine.upscale_single(img, T0Denoiser(321, 0.5), tile, tile, pad, blur, True)
+            del out
+        out = engine.upscale_single(img, T0Denoiser(123, 0.5), tile, tile, pad, blur, True)
+        assert _digest(out) == want
+    finally:
+        engine.FUSE_LEVELS = False

@@ -148,3 +148,41 @@ def test_generic_work_items_cover_every_output_once_and_fit_the_declared_patch(W
         assert listed == want, (bx, by)
         for j in range(first, first + count):
             assert (int(cover[j, 1]) & 0xFFFFFFFF) | (int(cover[j, 2]) << 32) == boffs[int(cover[j, 0])]
+
+
+@pytest.mark.parametrize("W,H,tile,pad,blur", [(1600, 1200, 512, 32, 8), (2048, 1536, 256, 32, 16), (7680, 4320, 512, 32, 8)])
+def test_level_worklists_order_every_crop_after_the_blends_it_reads(W, H, tile, pad, blur):
+    """usdu_level_blend_crop runs blend(wave k) and crop(wave k+1) in one grid; the planner's part is the dependency
+    slots of the crop records and the per-tile block counts.  For every pair of consecutive waves: a crop job names every
+    tile of wave k whose feather support intersects the canvas rectangle the job stages, and expect[slot] equals the
+    number of block chains that contain the tile (so the counters reach it exactly when the tile is fully composited)."""
+    p = planner.Plan.build(W, H, tile, tile, pad, blur, True)
+    if not p.mma:
+        pytest.skip("no tensor-core path")
+    waves = p.waves()
+    checked = 0
+    for k in range(len(waves) - 1):
+        offs, _ = p.slot_offsets(waves[k], 1)
+        r = p.level_worklist(waves[k], offs, waves[k + 1], 1)
+        assert r is not None
+        bl, cr, coffs, ctotal, expect = r
+        jb = bl.items.reshape(-1, nat.JOB_WORDS)
+        chains = np.zeros(len(waves[k]), dtype=np.int64)
+        for h in range(bl.n_launch):
+            i = h
+            while i >= 0:
+                chains[jb[i, nat.J_SLOT]] += 1
+                i = int(jb[i, nat.J_NEXT])
+        assert np.array_equal(chains, expect) and chains.sum() == jb.shape[0]
+        for J in cr.items.reshape(-1, nat.JOB_WORDS):
+            x0, y0 = int(J[nat.J_SRC_A]), int(J[nat.J_SRC_B])
+            rect = (x0, y0, x0 + int(J[nat.J_COLS]), y0 + int(J[nat.J_ROWS]))
+            deps = {int(J[w]) for w in (nat.J_CX0, nat.J_CX1, nat.J_CY0, nat.J_FLAGS) if J[w] >= 0}
+            for s, tid in enumerate(waves[k]):
+                t = p.tiles[tid]
+                sx0, sy0, sx1, sy1 = p.support(t)
+                sup = (t.x1 + sx0, t.y1 + sy0, t.x1 + sx1, t.y1 + sy1)
+                if sup[0] < rect[2] and rect[0] < sup[2] and sup[1] < rect[3] and rect[1] < sup[3]:
+                    assert s in deps, (k, tid, rect, sup)
+                    checked += 1
+    assert checked > 0
