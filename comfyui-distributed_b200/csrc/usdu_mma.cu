@@ -99,20 +99,28 @@ struct FragTable {
 // odd t gets n = 8 + 4(t/2)..+3 (tile B).  Returns the 4-group index within the 16 (0..3).
 __device__ __forceinline__ int pack16(const int (&dA)[3][4], const int (&dB)[3][4], int t, uint32_t (&word)[2]) {
     const bool odd = t & 1;
-    int keep[4], give[4];                       // [2 h + i]: the tile this lane keeps (A if even, B if odd) and the one it hands over
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int va = combine(dA[0][i], dA[1][i], dA[2][i]), vb = combine(dB[0][i], dB[1][i], dB[2][i]);
-        keep[i] = odd ? vb : va;
-        give[i] = odd ? va : vb;
-    }
-    const uint32_t send = pack2(give[0], give[1], pack2(give[2], give[3], 0));      // h = 0 pair low, h = 1 pair high
-    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    // even lanes: own pair = n 4j, 4j+1 (low half), partner's = 4j+2, 4j+3 (high half); odd lanes the other way round
-    const uint32_t k0 = pack2(keep[0], keep[1], 0), k1 = pack2(keep[2], keep[3], 0);
-    word[0] = odd ? __byte_perm(recv, k0, 0x5410) : __byte_perm(k0, recv, 0x5410);
-    word[1] = odd ? __byte_perm(recv, k1, 0x5432) : __byte_perm(k1, recv, 0x7610);
+    // both tiles packed first (h = 0 pair in the low half, h = 1 pair in the high half), THEN one select per role
+    const uint32_t pA = pack2(combine(dA[0][0], dA[1][0], dA[2][0]), combine(dA[0][1], dA[1][1], dA[2][1]),
+                              pack2(combine(dA[0][2], dA[1][2], dA[2][2]), combine(dA[0][3], dA[1][3], dA[2][3]), 0));
+    const uint32_t pB = pack2(combine(dB[0][0], dB[1][0], dB[2][0]), combine(dB[0][1], dB[1][1], dB[2][1]),
+                              pack2(combine(dB[0][2], dB[1][2], dB[2][2]), combine(dB[0][3], dB[1][3], dB[2][3]), 0));
+    const uint32_t keep = odd ? pB : pA;
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pA : pB, 1);
+    // even lanes: own pair = n 4j, 4j+1 (low bytes), partner's = 4j+2, 4j+3 (high bytes); odd lanes the other way round
+    const uint32_t lo = odd ? recv : keep, hi = odd ? keep : recv;
+    word[0] = __byte_perm(lo, hi, 0x5410);
+    word[1] = __byte_perm(lo, hi, 0x7632);
     return (t >> 1) + (odd ? 2 : 0);
+}
+
+// the same when only tile A carries data (the last 8 rows of a patch): even lanes still get 4 consecutive n of tile A,
+// odd lanes' words are meaningless (n = 8..15 do not exist) and must not be used
+__device__ __forceinline__ void pack8(const int (&dA)[3][4], int t, uint32_t (&word)[2]) {
+    const uint32_t pA = pack2(combine(dA[0][0], dA[1][0], dA[2][0]), combine(dA[0][1], dA[1][1], dA[2][1]),
+                              pack2(combine(dA[0][2], dA[1][2], dA[2][2]), combine(dA[0][3], dA[1][3], dA[2][3]), 0));
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, pA, 1);
+    word[0] = __byte_perm(pA, recv, 0x5410);
+    word[1] = __byte_perm(pA, recv, 0x7632);
 }
 
 __device__ __forceinline__ void init_acc(int (&d)[3][4]) {
@@ -135,22 +143,25 @@ struct HGeo {
 // ---- H pass: planes -> mid (row-packed) ---------------------------------------------------------------------------
 template <int KS>
 __device__ __forceinline__ void hpass(const uint8_t* __restrict__ planes, uint32_t* __restrict__ mid, const int32_t* __restrict__ tabs,
-                                      const JobView& J, int PB, int plane_rows, int steps16) {
+                                      const JobView& J, int PB, int plane_rows, int rows) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const FragTable F(tabs, J[USDU_J_ROWS_H]);
     const HGeo G(J);
     const int sx0 = J[USDU_J_IX0];
+    const int full = rows >> 4;                                 // steps of 16 rows with both N-tiles
+    const int tail = rows & 15;                                 // 1..8 rows left: tile A only; 9..15: one more full step
+    const int steps = full + (tail > 8 ? 1 : 0);
     for (int mt = G.mt0 + w; mt <= G.mt1; mt += kT / 32) {
         uint32_t a[KS][3][4];
         F.load<KS>(a, mt, lane);
         const int krel = F.k0(mt) - sx0;                       // >= 0, multiple of 4
-        const int col0 = 3 * ((mt << 4) + g - G.o_org);
+        uint32_t* mcol = mid + 3 * ((mt << 4) + g - G.o_org);
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
-            const uint8_t* pl = planes + (size_t)c * plane_rows * PB + krel + 4 * t + g * PB;
+            const uint8_t* pa = planes + (size_t)c * plane_rows * PB + krel + 4 * t + g * PB;
+            uint32_t* mo = mcol + c;
 #pragma unroll 1
-            for (int s = 0; s < steps16; ++s) {
-                const uint8_t* pa = pl + (size_t)(16 * s) * PB;
+            for (int s = 0; s < steps; ++s, pa += 16 * PB, mo += 4 * MIDP) {
                 int dA[3][4], dB[3][4];
                 init_acc(dA); init_acc(dB);
 #pragma unroll
@@ -161,17 +172,33 @@ __device__ __forceinline__ void hpass(const uint8_t* __restrict__ planes, uint32
                     mma_uu(dB[0], a[ks][0], b0, b1); mma_uu(dB[1], a[ks][1], b0, b1); mma_su(dB[2], a[ks][2], b0, b1);
                 }
                 uint32_t word[2];
-                const int kg = 4 * s + pack16(dA, dB, t, word);  // 4 consecutive ROWS of outputs m = g (word 0) and g + 8 (word 1)
-                mid[kg * MIDP + col0 + c] = word[0];
-                mid[kg * MIDP + col0 + 24 + c] = word[1];
+                const int kg = pack16(dA, dB, t, word);          // 4 consecutive ROWS of outputs m = g (word 0) and g + 8 (word 1)
+                mo[kg * MIDP] = word[0];
+                mo[kg * MIDP + 24] = word[1];
+            }
+            if (tail >= 1 && tail <= 8) {                        // the last <= 8 rows: half the MMAs, half the recombination
+                int dA[3][4];
+                init_acc(dA);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa + 32 * ks), a1 = *reinterpret_cast<const uint32_t*>(pa + 32 * ks + 16);
+                    mma_uu(dA[0], a[ks][0], a0, a1); mma_uu(dA[1], a[ks][1], a0, a1); mma_su(dA[2], a[ks][2], a0, a1);
+                }
+                uint32_t word[2];
+                pack8(dA, t, word);
+                if (!(t & 1)) {                                  // rows 4 (t/2) .. + 3 of this last group of 8
+                    mo[(t >> 1) * MIDP] = word[0];
+                    mo[(t >> 1) * MIDP + 24] = word[1];
+                }
             }
         }
     }
 }
 
 // ---- V pass: mid -> 4-byte strips of block rows, handed to an epilogue -----------------------------------------------
-// Epilogue::prefetch(r0, r1, strip) issues the loads the epilogue will need for block rows r0, r1 BEFORE the MMAs;
-// Epilogue::store(pre, h, r, strip, word) consumes them (bytes 4 strip .. 4 strip + 3 of block row r).
+// Epilogue::rows(r0, r1) fixes the two block rows of the M-tile's halves (m = g and g + 8) once per M-tile;
+// Epilogue::prefetch(strip) issues the loads the epilogue will need BEFORE the MMAs;
+// Epilogue::store(pre, h, strip, word) consumes them (bytes 4 strip .. 4 strip + 3 of row half h).
 template <int KS, class Epilogue>
 __device__ __forceinline__ void vpass(const uint32_t* __restrict__ mid, const int32_t* __restrict__ tabs, const JobView& J, int bh,
                                       Epilogue& epi) {
@@ -180,36 +207,33 @@ __device__ __forceinline__ void vpass(const uint32_t* __restrict__ mid, const in
     const HGeo G(J);
     const int oyb = J[USDU_J_OY_BASE], sy0 = J[USDU_J_IY0];
     const int mv0 = max(oyb, 0) >> 4, mv1 = (min(oyb + bh, J[USDU_J_N_OUT_V]) - 1) >> 4;
-    constexpr int PAIRS = BWX * 3 / 16;                        // 24 pairs of N-tiles = 384 byte columns
-    const int units = (mv1 - mv0 + 1) * PAIRS;
-    int cur = -1, kgbase = 0;
-    uint32_t a[KS][3][4];
+    constexpr int PAIRS = BWX * 3 / 16;                        // 24 pairs of N-tiles = 384 byte columns: 3 per warp
     const int sub = (t >> 1) + ((t & 1) ? 2 : 0);               // which 4-byte strip of the pair this lane ends with
 #pragma unroll 1
-    for (int u = w; u < units; u += kT / 32) {
-        const int mv = mv0 + u / PAIRS, p = u - (u / PAIRS) * PAIRS;
-        if (mv != cur) {
-            F.load<KS>(a, mv, lane);
-            kgbase = (F.k0(mv) - sy0) >> 2;
-            cur = mv;
-        }
+    for (int mv = mv0; mv <= mv1; ++mv) {
+        uint32_t a[KS][3][4];
+        F.load<KS>(a, mv, lane);
         const int r0 = (mv << 4) + g - oyb;                     // block row of output m = g; m = g + 8 is r0 + 8
-        const int strip = 4 * p + sub;
-        const typename Epilogue::Pre pre = epi.prefetch(r0, r0 + 8, strip);
-        const uint32_t* mp = mid + (kgbase + t) * MIDP + G.coff + 16 * p + g;
-        int dA[3][4], dB[3][4];
-        init_acc(dA); init_acc(dB);
+        epi.rows(r0, r0 + 8);
+        const uint32_t* mp = mid + (((F.k0(mv) - sy0) >> 2) + t) * MIDP + G.coff + g + 16 * w;
+        int strip = 4 * w + sub;
+#pragma unroll 1
+        for (int p = w; p < PAIRS; p += kT / 32, mp += 16 * (kT / 32), strip += 4 * (kT / 32)) {
+            const typename Epilogue::Pre pre = epi.prefetch(strip);
+            int dA[3][4], dB[3][4];
+            init_acc(dA); init_acc(dB);
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const uint32_t a0 = mp[(8 * ks) * MIDP], a1 = mp[(8 * ks + 4) * MIDP];
-            const uint32_t b0 = mp[(8 * ks) * MIDP + 8], b1 = mp[(8 * ks + 4) * MIDP + 8];
-            mma_uu(dA[0], a[ks][0], a0, a1); mma_uu(dA[1], a[ks][1], a0, a1); mma_su(dA[2], a[ks][2], a0, a1);
-            mma_uu(dB[0], a[ks][0], b0, b1); mma_uu(dB[1], a[ks][1], b0, b1); mma_su(dB[2], a[ks][2], b0, b1);
+            for (int ks = 0; ks < KS; ++ks) {
+                const uint32_t a0 = mp[(8 * ks) * MIDP], a1 = mp[(8 * ks + 4) * MIDP];
+                const uint32_t b0 = mp[(8 * ks) * MIDP + 8], b1 = mp[(8 * ks + 4) * MIDP + 8];
+                mma_uu(dA[0], a[ks][0], a0, a1); mma_uu(dA[1], a[ks][1], a0, a1); mma_su(dA[2], a[ks][2], a0, a1);
+                mma_uu(dB[0], a[ks][0], b0, b1); mma_uu(dB[1], a[ks][1], b0, b1); mma_su(dB[2], a[ks][2], b0, b1);
+            }
+            uint32_t word[2];
+            pack16(dA, dB, t, word);                            // 4 consecutive BYTES of block rows r0 (word 0) and r0 + 8 (word 1)
+            epi.store(pre, 0, strip, word[0]);
+            epi.store(pre, 1, strip, word[1]);
         }
-        uint32_t word[2];
-        pack16(dA, dB, t, word);                                // 4 consecutive BYTES of block rows r0 (word 0) and r0 + 8 (word 1)
-        epi.store(pre, 0, r0, strip, word[0]);
-        epi.store(pre, 1, r0 + 8, strip, word[1]);
     }
 }
 
@@ -229,19 +253,25 @@ __device__ __forceinline__ void deinterleave(uint32_t w0, uint32_t w1, uint32_t 
     B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);      // bytes 2 5 8 11
 }
 
+// i / d for 0 <= i < 2^16, 1 <= d < 2^16 without a division: m = floor(2^32 / d) + 1
+// (d == 1 wraps m to 0, which stands for "i itself")
+__device__ __forceinline__ uint32_t recip_u16(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
+__device__ __forceinline__ int div_u16(int i, uint32_t m) { return m ? (int)__umulhi((uint32_t)i, m) : i; }
+
 // fp32 source in [0,1] (sampler output): Q1 truncation on the fly.  src -> first float of the staged patch.
 // kU units per thread per trip, every load issued before the first use (12 x 16 bytes in flight per thread).
 __device__ __forceinline__ void stage_f32(uint8_t* planes, int PB, int plane_rows, const float* __restrict__ src, int64_t pitch_f,
                                           int rows, int cols) {
     constexpr int kU = 3;
     const int chunks = cols >> 2, total = rows * chunks;
+    const uint32_t rc = recip_u16(chunks);
     for (int i0 = threadIdx.x; i0 < total; i0 += kT * kU) {
         float4 f[kU][3];
         int rr[kU], cc[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const int i = min(i0 + u * kT, total - 1);
-            rr[u] = i / chunks; cc[u] = i - rr[u] * chunks;
+            rr[u] = div_u16(i, rc); cc[u] = i - rr[u] * chunks;
             const float4* p = reinterpret_cast<const float4*>(src + (int64_t)rr[u] * pitch_f) + cc[u] * 3;
             f[u][0] = __ldg(p); f[u][1] = __ldg(p + 1); f[u][2] = __ldg(p + 2);
         }
@@ -262,13 +292,14 @@ __device__ __forceinline__ void stage_u8(uint8_t* planes, int PB, int plane_rows
                                          int rows, int cols) {
     constexpr int kU = 4;
     const int chunks = cols >> 2, total = rows * chunks;
+    const uint32_t rc = recip_u16(chunks);
     for (int i0 = threadIdx.x; i0 < total; i0 += kT * kU) {
         uint32_t w[kU][3];
         int rr[kU], cc[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const int i = min(i0 + u * kT, total - 1);
-            rr[u] = i / chunks; cc[u] = i - rr[u] * chunks;
+            rr[u] = div_u16(i, rc); cc[u] = i - rr[u] * chunks;
             const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (int64_t)rr[u] * pitch) + cc[u] * 3;
             w[u][0] = __ldg(p); w[u][1] = __ldg(p + 1); w[u][2] = __ldg(p + 2);
         }
@@ -285,8 +316,9 @@ __device__ __forceinline__ void stage_u8(uint8_t* planes, int PB, int plane_rows
 // the same from the two TMA boxes in shared memory (virtual 512-byte rows); lead_b = bytes before the first pixel
 __device__ __forceinline__ void stage_raw(uint8_t* planes, int PB, int plane_rows, const uint8_t* raw, int rows, int cols, int lead_b) {
     const int chunks = cols >> 2;
+    const uint32_t rc = recip_u16(chunks);
     for (int i = threadIdx.x; i < rows * chunks; i += kT) {
-        const int r = i / chunks, ch = i - r * chunks;
+        const int r = div_u16(i, rc), ch = i - r * chunks;
         uint32_t w[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -303,9 +335,9 @@ __device__ __forceinline__ void stage_raw(uint8_t* planes, int PB, int plane_row
 template <int KSMAX, class Epilogue>
 __device__ __forceinline__ void both_passes(const uint8_t* planes, uint32_t* mid, const int32_t* tabs, const JobView& J, int PB,
                                             int plane_rows, int bh, Epilogue& epi) {
-    const int steps16 = (J[USDU_J_ROWS] + 15) >> 4;
-    if (KSMAX == 1 || J[USDU_J_TAPS_H] <= 1) hpass<1>(planes, mid, tabs, J, PB, plane_rows, steps16);
-    else hpass<KSMAX>(planes, mid, tabs, J, PB, plane_rows, steps16);
+    const int rows = J[USDU_J_ROWS];
+    if (KSMAX == 1 || J[USDU_J_TAPS_H] <= 1) hpass<1>(planes, mid, tabs, J, PB, plane_rows, rows);
+    else hpass<KSMAX>(planes, mid, tabs, J, PB, plane_rows, rows);
     __syncthreads();
     if (KSMAX == 1 || J[USDU_J_TAPS_V] <= 1) vpass<1>(mid, tabs, J, bh, epi);
     else vpass<KSMAX>(mid, tabs, J, bh, epi);
@@ -318,16 +350,21 @@ struct CropEpilogue {
     float* dst;          // &out[tile][b][oy0][ox0][0]
     int64_t row_pitch;   // floats per output row
     int ow3, rows_out;
+    float* rp[2];        // row pointers of the current M-tile halves (nullptr = row outside the block)
     struct Pre {};
-    __device__ __forceinline__ Pre prefetch(int, int, int) const { return Pre{}; }
-    __device__ __forceinline__ void store(const Pre&, int, int r, int strip, uint32_t v) {
-        if (r >= 0 && r < rows_out && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
+    __device__ __forceinline__ void rows(int r0, int r1) {
+        rp[0] = (r0 >= 0 && r0 < rows_out) ? dst + (int64_t)r0 * row_pitch : nullptr;
+        rp[1] = (r1 >= 0 && r1 < rows_out) ? dst + (int64_t)r1 * row_pitch : nullptr;
+    }
+    __device__ __forceinline__ Pre prefetch(int) const { return Pre{}; }
+    __device__ __forceinline__ void store(const Pre&, int h, int strip, uint32_t v) {
+        if (rp[h] != nullptr && 4 * strip < ow3) {   // ow3 is a multiple of 4 (pw % 8 == 0)
             // u / 255.0f in arithmetic (dequant_u8_fast): a 256-entry table in shared memory costs 4 data-dependent loads per
             // thread that collide on banks -- 78 % of the kernel's excess shared-memory wavefronts in the r02e profile
             float4 o;
             o.x = dequant_u8_fast(v & 0xFF); o.y = dequant_u8_fast((v >> 8) & 0xFF);
             o.z = dequant_u8_fast((v >> 16) & 0xFF); o.w = dequant_u8_fast(v >> 24);
-            __stcs(reinterpret_cast<float4*>(dst + (int64_t)r * row_pitch + 4 * strip), o);
+            __stcs(reinterpret_cast<float4*>(rp[h] + 4 * strip), o);
         }
     }
 };
@@ -391,21 +428,25 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
 struct DTile {
     uint8_t* base;
     int bh;                                  // rows per box
-    __device__ __forceinline__ uint32_t* word(int r, int strip) const {
-        const int col = 4 * strip;
-        const int box = col >= kDBox ? 1 : 0;
-        return reinterpret_cast<uint32_t*>(base + (size_t)box * bh * kDBox + r * kDBox + (col - box * kDBox));
+    // byte offset of strip `strip` inside a row of the two-box block (box 1 starts bh * 192 bytes after box 0)
+    __device__ __forceinline__ int strip_off(int strip) const {
+        return 4 * strip + (strip >= kDBox / 4 ? bh * kDBox - kDBox : 0);
     }
 };
 
 // interior of a tile (alpha == 255 over the whole block): the canvas block becomes S
 struct BlendOpaque {
     DTile d;
-    int rows;
+    int nrows;
+    uint8_t* rp[2];
     struct Pre {};
-    __device__ __forceinline__ Pre prefetch(int, int, int) const { return Pre{}; }
-    __device__ __forceinline__ void store(const Pre&, int, int r, int strip, uint32_t v) {
-        if (r >= 0 && r < rows) *d.word(r, strip) = v;
+    __device__ __forceinline__ void rows(int r0, int r1) {
+        rp[0] = (r0 >= 0 && r0 < nrows) ? d.base + r0 * kDBox : nullptr;
+        rp[1] = (r1 >= 0 && r1 < nrows) ? d.base + r1 * kDBox : nullptr;
+    }
+    __device__ __forceinline__ Pre prefetch(int) const { return Pre{}; }
+    __device__ __forceinline__ void store(const Pre&, int h, int strip, uint32_t v) {
+        if (rp[h] != nullptr) *reinterpret_cast<uint32_t*>(rp[h] + d.strip_off(strip)) = v;
     }
 };
 
@@ -415,11 +456,20 @@ struct BlendFeather {
     const uint8_t* mask;   // template address of block pixel (0,0) (may point outside; guarded by the rect)
     int mpitch;
     int cx0, cx1, cy0, cy1;   // sub-rect in block pixel coordinates
+    uint8_t* rp[2];           // canvas-block rows of the current M-tile halves (nullptr = outside [cy0, cy1))
+    const uint8_t* mp[2];     // their template rows
     struct Pre {
         uint32_t aa[2], ab[2];   // per row half: alpha of the two pixels the 4 bytes touch
         int split;               // bytes [0, split) belong to the first pixel
     };
-    __device__ __forceinline__ Pre prefetch(int r0, int r1, int strip) const {
+    __device__ __forceinline__ void rows(int r0, int r1) {
+        const bool in0 = r0 >= cy0 && r0 < cy1, in1 = r1 >= cy0 && r1 < cy1;
+        rp[0] = in0 ? d.base + r0 * kDBox : nullptr;
+        rp[1] = in1 ? d.base + r1 * kDBox : nullptr;
+        mp[0] = mask + (int64_t)r0 * mpitch;
+        mp[1] = mask + (int64_t)r1 * mpitch;
+    }
+    __device__ __forceinline__ Pre prefetch(int strip) const {
         const int col = 4 * strip;
         const int pa = col / 3, pb = (col + 3) / 3;          // pb = pa or pa + 1
         const bool ina = pa >= cx0 && pa < cx1, inb = pb >= cx0 && pb < cx1;
@@ -427,18 +477,15 @@ struct BlendFeather {
         p.split = 3 * pb - col;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int r = h ? r1 : r0;
-            const bool inr = r >= cy0 && r < cy1;
-            const uint8_t* mrow = mask + (int64_t)r * mpitch;
-            p.aa[h] = (inr && ina) ? (uint32_t)__ldg(mrow + pa) : 0u;
-            p.ab[h] = (inr && inb) ? (uint32_t)__ldg(mrow + pb) : 0u;
+            p.aa[h] = (rp[h] != nullptr && ina) ? (uint32_t)__ldg(mp[h] + pa) : 0u;
+            p.ab[h] = (rp[h] != nullptr && inb) ? (uint32_t)__ldg(mp[h] + pb) : 0u;
         }
         return p;
     }
-    __device__ __forceinline__ void store(const Pre& p, int h, int r, int strip, uint32_t v) {
+    __device__ __forceinline__ void store(const Pre& p, int h, int strip, uint32_t v) {
         const uint32_t aa = p.aa[h], ab = p.ab[h];
         if ((aa | ab) == 0u) return;                         // also: rows outside [cy0, cy1)
-        uint32_t* w = d.word(r, strip);
+        uint32_t* w = reinterpret_cast<uint32_t*>(rp[h] + d.strip_off(strip));
         if ((aa & ab) == 255u) { *w = v; return; }
         const uint32_t dv = *w;
         uint32_t o = 0;
@@ -497,7 +544,7 @@ blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ m
         if (J[USDU_J_FLAGS] & 1) {
             BlendOpaque epi;
             epi.d = D;
-            epi.rows = J[USDU_J_ROWS_OUT];
+            epi.nrows = J[USDU_J_ROWS_OUT];
             both_passes<KSMAX>(planes, mid, tabs, J, PB, plane_rows, block_rows, epi);
         } else {
             BlendFeather epi;
@@ -604,7 +651,7 @@ level_mma_kernel(const __grid_constant__ LevelArgs a) {
             if (J[USDU_J_FLAGS] & 1) {
                 BlendOpaque epi;
                 epi.d = D;
-                epi.rows = J[USDU_J_ROWS_OUT];
+                epi.nrows = J[USDU_J_ROWS_OUT];
                 both_passes<KSMAX>(planes, mid, a.tabs, J, PB, a.b_plane_rows, block_rows, epi);
             } else {
                 BlendFeather epi;
