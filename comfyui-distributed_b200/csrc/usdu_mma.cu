@@ -27,7 +27,7 @@ namespace mma {
 
 constexpr int kT = 256;                     // 8 warps
 #ifndef USDU_MMA_CTAS
-#define USDU_MMA_CTAS 3                      // resident CTAs per SM the kernels are compiled for: 80 registers, no spills; 4 (64 registers,
+#define USDU_MMA_CTAS 4                      // resident CTAs per SM the kernels are compiled for: 80 registers, no spills; 4 (64 registers,
                                              // 92 B of spills in the feather V pass) is faster for the crop alone at full launches (244 vs 260 us
                                              // for all 135 tiles of cfg2) but slower inside the 31-wave job (profiles/r02f_kernel_bench_*.txt)
 #endif
@@ -380,7 +380,7 @@ crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const 
     extern __shared__ __align__(128) uint8_t smem[];
     // [mid | raw (TMA boxes), aliased: raw is dead before the H pass writes mid] [job] [bar] [planes]
     constexpr bool kTma = kSrc == 1;
-    const size_t region = kTma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);
+    const size_t region = kTma ? max(mid_bytes(mid_rows), (size_t)2 * kBoxR * kBoxB) : mid_bytes(mid_rows);   // (boxes are always 48 rows)
     uint32_t* mid = reinterpret_cast<uint32_t*>(smem);
     uint8_t* raw = smem;
     int32_t* job_sm = reinterpret_cast<int32_t*>(smem + region);
@@ -504,12 +504,13 @@ blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ m
                  const void* __restrict__ src_v, int W3, int patch_w, int plane_rows, int mid_rows, int block_rows,
                  const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // [canvas block: 2 boxes x block_rows x 192] [job] [bar] [planes] [mid]
+    // [canvas block: 2 boxes x block_rows x 192] [job] [bar] [mid] [planes]   (planes BEHIND mid: the vertical K windows may
+    // read a few row groups past the rows the horizontal pass wrote -- zero coefficients -- and must stay inside the CTA's memory)
     const size_t dbytes = (size_t)2 * block_rows * kDBox;
     int32_t* job_sm = reinterpret_cast<int32_t*>(smem + dbytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dbytes + kHeadBytes);
-    uint8_t* planes = smem + dbytes + kHeadBytes + 16;
-    uint32_t* mid = reinterpret_cast<uint32_t*>(planes + planes_bytes(patch_w, plane_rows));
+    uint32_t* mid = reinterpret_cast<uint32_t*>(smem + dbytes + kHeadBytes + 16);
+    uint8_t* planes = smem + dbytes + kHeadBytes + 16 + mid_bytes(mid_rows);
     const int PB = plane_pitch(patch_w);
     const int b = blockIdx.y;
     const JobView J{job_sm};
@@ -621,8 +622,8 @@ level_mma_kernel(const __grid_constant__ LevelArgs a) {
         const size_t dbytes = (size_t)2 * block_rows * kDBox;
         int32_t* job_sm = reinterpret_cast<int32_t*>(smem + dbytes);
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + dbytes + kHeadBytes);
-        uint8_t* planes = smem + dbytes + kHeadBytes + 16;
-        uint32_t* mid = reinterpret_cast<uint32_t*>(planes + planes_bytes(a.b_patch_w, a.b_plane_rows));
+        uint32_t* mid = reinterpret_cast<uint32_t*>(smem + dbytes + kHeadBytes + 16);
+        uint8_t* planes = smem + dbytes + kHeadBytes + 16 + mid_bytes(a.b_mid_rows);
         const int PB = plane_pitch(a.b_patch_w);
         const JobView J{job_sm};
         DTile D{smem, block_rows};
@@ -758,8 +759,8 @@ static int optin(const void* fn, size_t bytes) {
 static int split_patch_h(int patch_h, int* plane_rows, int* mid_rows, const char* who) {
     *plane_rows = patch_h & 0xFFFF;
     *mid_rows = (patch_h >> 16) & 0xFFFF;
-    if (*plane_rows <= 0 || *plane_rows % 16 || *mid_rows < *plane_rows || *mid_rows % 4) {
-        set_error("%s: with USDU_FLAG_MMA patch_h carries plane rows (x16) in bits 0..15 and intermediate rows (x4, >= plane rows) "
+    if (*plane_rows <= 0 || *plane_rows % 8 || *mid_rows < *plane_rows || *mid_rows % 4) {
+        set_error("%s: with USDU_FLAG_MMA patch_h carries plane rows (x8) in bits 0..15 and intermediate rows (x4, >= plane rows) "
                   "in bits 16..31; got %d / %d", who, *plane_rows, *mid_rows);
         return USDU_ERR_INVALID;
     }

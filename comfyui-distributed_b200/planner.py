@@ -683,14 +683,22 @@ class Plan:
         J[:, nat.J_FRAME_LO], J[:, nat.J_FRAME_HI] = frame & 0xFFFFFFFF, frame >> 32
         J[:, nat.J_NEXT] = -1
         J[:, nat.J_CY1] = bh                                        # block height (rows per CTA)
-        return J, int(max(cols.max(), need_w.max())), self._mma_patch_h(rws, need_h)
+        pw_ = int(max(cols.max(), need_w.max()))
+        return J, pw_, self._mma_patch_h(rws, need_h, pw_)
 
     @staticmethod
-    def _mma_patch_h(rws: np.ndarray, need_h: np.ndarray) -> int:
-        """patch_h word of a tensor-core launch: plane rows (staged rows up to a multiple of 16: the horizontal pass
-        runs 16 rows per step) in bits 0..15, rows of the intermediate (what the vertical K windows reach) in 16..31."""
-        plane_rows = int((rws.max() + 15) // 16 * 16)
-        mid_rows = int((max(plane_rows, int(need_h.max())) + 3) // 4 * 4)
+    def _mma_patch_h(rws: np.ndarray, need_h: np.ndarray, patch_w: int = 0) -> int:
+        """patch_h word of a tensor-core launch: plane rows in bits 0..15 -- the staged rows up to a multiple of 8 (the
+        horizontal pass runs 16 rows per step and finishes with an 8-row step when <= 8 rows are left) --, rows of the
+        intermediate the kernel ALLOCATES in bits 16..31.  The horizontal pass writes plane_rows rows of it; the K window of
+        the last vertical M-tile may reach further (need_h), but only with zero coefficients, and the kernels lay the byte
+        planes out right BEHIND the intermediate, so those reads land in the planes: the allocation stops at the written
+        rows whenever the overrun fits there (it always does for one-k-step axes)."""
+        plane_rows = int((rws.max() + 7) // 8 * 8)
+        need = int((max(plane_rows, int(need_h.max())) + 3) // 4 * 4)
+        overrun_bytes = (need - plane_rows) // 4 * 440 * 4
+        planes_bytes = 3 * plane_rows * ((patch_w + 31) // 32 * 32 + 16)
+        mid_rows = plane_rows if overrun_bytes <= planes_bytes else need
         return plane_rows | (mid_rows << 16)
 
     def _first(self, key: Tuple[int, int], idx: np.ndarray) -> np.ndarray:
@@ -878,7 +886,8 @@ class Plan:
         out = np.zeros_like(J)
         out[pos] = J
         if mma:
-            return out, int(max((ix1 - ix0).max(), need_w.max())), self._mma_patch_h(iy1 - iy0, need_h)
+            pw_ = int(max((ix1 - ix0).max(), need_w.max()))
+            return out, pw_, self._mma_patch_h(iy1 - iy0, need_h, pw_)
         return out
 
 

@@ -194,7 +194,9 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
  * USDU_J_TAPS_H / _V = k-steps (1 or 2), USDU_J_IX0 / _IY0 = first staged input column / row (multiples of 4),
  * USDU_J_COLS a multiple of 4, USDU_J_LEAD = 0, crop: USDU_J_SRC_A a multiple of 4 and USDU_J_CY1 = block rows (16 / 32).
  * patch_w = bytes a plane row must hold (staged pixels or the reach of the last K window, whichever is larger);
- * patch_h = plane rows (multiple of 16) in bits 0..15, rows of the intermediate (multiple of 4) in bits 16..31.
+ * patch_h = plane rows (multiple of 8) in bits 0..15, rows of the intermediate the kernel allocates (multiple of 4, >= plane
+ * rows) in bits 16..31; the byte planes lie right behind the intermediate in shared memory, so vertical K windows may reach
+ * past the allocated rows (zero coefficients) as long as they stay inside the planes.
  * usdu_tile_blend: block height 16 or 32 in flags bits 8..15. */
 #define USDU_FLAG_MMA 2
 /* ... some record of the launch has USDU_J_TAPS_H or _V == 2 (an axis scaled by more than ~1.4): run the two-k-step build */

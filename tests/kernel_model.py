@@ -176,30 +176,34 @@ def _mma_passes(plan, J, staged, wl, rng):
     patch_w, plane_rows, mid_rows = wl.patch_w, wl.patch_h & 0xFFFF, wl.patch_h >> 16
     PB = _plane_pitch(patch_w)
     rows, cols = staged.shape[:2]
-    assert cols % 4 == 0 and cols <= PB and rows <= plane_rows and plane_rows % 16 == 0 and mid_rows % 4 == 0
+    assert cols % 4 == 0 and cols <= PB and rows <= plane_rows and plane_rows % 8 == 0 and mid_rows % 4 == 0 and mid_rows >= plane_rows
     planes = rng.integers(0, 256, (3, plane_rows, PB)).astype(np.int64)
     planes[:, :rows, :cols] = np.moveaxis(staged, 2, 0)
-    mid = rng.integers(0, 256, (mid_rows, MIDP_BYTES)).astype(np.int64)
+    # the kernels keep the planes right behind the intermediate: vertical K windows may read past the allocated rows into
+    # them (zero coefficients); model that memory as more garbage rows and check the overrun stays inside the planes
+    planes_bytes = 3 * plane_rows * PB
+    mid = rng.integers(0, 256, (mid_rows + planes_bytes // (MIDP_BYTES * 4) * 4, MIDP_BYTES)).astype(np.int64)
     oxb, n_out_h = int(J[nat.J_OX_BASE]), int(J[nat.J_N_OUT_H])
     mt0, mt1 = max(oxb, 0) >> 4, (min(oxb + nat.FAST_BLOCK_W, n_out_h) - 1) >> 4
     o_org = min(oxb, mt0 << 4)
     coff = 3 * (oxb - o_org)
     sx0, sy0 = int(J[nat.J_IX0]), int(J[nat.J_IY0])
     assert sx0 % 4 == 0 and sy0 % 4 == 0
-    steps16 = (rows + 15) >> 4
+    full, tail = rows >> 4, rows & 15
+    hrows = 16 * full + (0 if tail == 0 else 8 if tail <= 8 else 16)     # 16-row steps, then an 8-row step for a short tail
+    assert hrows <= plane_rows and hrows <= mid_rows
     for mt in range(mt0, mt1 + 1):
         k0, A, ks = _frag(tabs, int(J[nat.J_ROWS_H]), mt)
         assert ks == int(J[nat.J_TAPS_H])
         krel = k0 - sx0
         assert krel >= 0 and krel % 4 == 0 and krel + 32 * ks <= PB, (krel, ks, PB)
         for c in range(3):
-            X = planes[c, :16 * steps16, krel:krel + 32 * ks]                    # [rows16, K]
-            out = np.clip(((A @ X.T) + (1 << 21)) >> 22, 0, 255)                  # [16 m, rows16]
+            X = planes[c, :hrows, krel:krel + 32 * ks]                             # [hrows, K]
+            out = np.clip(((A @ X.T) + (1 << 21)) >> 22, 0, 255)                  # [16 m, hrows]
             for m in range(16):
                 col = 3 * ((mt << 4) + m - o_org) + c
                 assert 0 <= col < MIDP_BYTES
-                assert 16 * steps16 <= mid_rows
-                mid[:16 * steps16, col] = out[m]
+                mid[:hrows, col] = out[m]
     oyb, n_out_v = int(J[nat.J_OY_BASE]), int(J[nat.J_N_OUT_V])
     bh = wl.block_rows if wl.block_rows else int(J[nat.J_CY1])
     mv0, mv1 = max(oyb, 0) >> 4, (min(oyb + bh, n_out_v) - 1) >> 4
@@ -208,7 +212,7 @@ def _mma_passes(plan, J, staged, wl, rng):
         k0, A, ks = _frag(tabs, int(J[nat.J_ROWS_V]), mv)
         assert ks == int(J[nat.J_TAPS_V])
         kg0 = k0 - sy0
-        assert kg0 >= 0 and kg0 % 4 == 0 and kg0 + 32 * ks <= mid_rows, (kg0, ks, mid_rows)
+        assert kg0 >= 0 and kg0 % 4 == 0 and kg0 + 32 * ks <= mid.shape[0], (kg0, ks, mid_rows, mid.shape[0])
         assert coff + 384 <= MIDP_BYTES
         X = mid[kg0:kg0 + 32 * ks, coff:coff + 384]                                # [K, 384]
         out = np.clip(((A @ X) + (1 << 21)) >> 22, 0, 255)                        # [16, 384]
