@@ -26,11 +26,12 @@ namespace usdu {
 namespace mma {
 
 constexpr int kT = 256;                     // 8 warps
-#ifndef USDU_MMA_CTAS
-#define USDU_MMA_CTAS 4                      // resident CTAs per SM the kernels are compiled for: 80 registers, no spills; 4 (64 registers,
-                                             // 92 B of spills in the feather V pass) is faster for the crop alone at full launches (244 vs 260 us
-                                             // for all 135 tiles of cfg2) but slower inside the 31-wave job (profiles/r02f_kernel_bench_*.txt)
-#endif
+// Resident CTAs per SM the kernels are compiled for.  3 = 80 registers, no spills: the faster build inside the 31-wave job,
+// where launches are 1-8 tiles and per-thread speed counts (cfg2: 1.222 vs 1.270 ms).  4 = 64 registers: more warps to hide the
+// staging latency, the faster build for the CROP on machine-filling launches (all 135 tiles: 216 vs 234 us); the blend gains
+// nothing from it (331 vs 333 us).  The crop launcher picks by grid size; profiles/r02n_*, r02o_*.
+constexpr int kOccSmall = 3, kOccLarge = 4;
+constexpr int kLargeGrid = 148 * 8;          // CTAs from which the 4-CTA build of the crop is used
 constexpr int BWX = USDU_FAST_BLOCK_W;      // 128-pixel wide blocks
 constexpr int MIDP = 440;                   // words per row group of the intermediate: >= 3 * 144 columns, == 24 mod 32
 constexpr int kDBox = BWX * 3 / 2;          // canvas block = two bulk-tensor boxes of 192 bytes per row
@@ -372,8 +373,8 @@ struct CropEpilogue {
 // kSrc: 0 = u8 canvas read with LDG, 1 = u8 canvas staged by TMA, 2 = the fp32 IMAGE itself (`canvas` is then a float
 // pointer and `pitch` counts floats per row): Q0's truncating cast happens while staging, the window is bit-identical
 // to cropping the quantised canvas -- a rank of a conflict-free partition never needs the quantised canvas at all.
-template <int kSrc, int KSMAX>
-__global__ void __launch_bounds__(kT, KSMAX == 1 ? USDU_MMA_CTAS : 3)
+template <int kSrc, int KSMAX, int kOcc>
+__global__ void __launch_bounds__(kT, KSMAX == 1 ? kOcc : 3)
 crop_mma_kernel(const uint8_t* __restrict__ canvas, int H, int64_t pitch, const int32_t* __restrict__ tabs,
                 const int32_t* __restrict__ jobs, float* __restrict__ out, int patch_w, int plane_rows, int mid_rows, int W3,
                 const __grid_constant__ CUtensorMap cmap) {
@@ -499,7 +500,7 @@ struct BlendFeather {
 };
 
 template <bool kSrcU8, int KSMAX>
-__global__ void __launch_bounds__(kT, KSMAX == 1 ? USDU_MMA_CTAS : 3)
+__global__ void __launch_bounds__(kT, kOccSmall)
 blend_mma_kernel(const int32_t* __restrict__ tabs, const uint8_t* __restrict__ mask_pool, const int32_t* __restrict__ jobs,
                  const void* __restrict__ src_v, int W3, int patch_w, int plane_rows, int mid_rows, int block_rows,
                  const __grid_constant__ CUtensorMap cmap) {
@@ -786,24 +787,26 @@ int launch_crop(const void* canvas, int src_f32, int B, int H, int W, int64_t pi
     const uint8_t* cv = static_cast<const uint8_t*>(canvas);
     const dim3 grid(n_items, B);
     const int W3 = W * 3;
+    const bool large = (int64_t)n_items * B >= kLargeGrid && !two_ksteps;
+#define USDU_CROP_LAUNCH(SRC)                                                                                                                   \
+    (two_ksteps ? launch_one(crop_mma_kernel<SRC, 2, kOccSmall>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap) \
+     : large    ? launch_one(crop_mma_kernel<SRC, 1, kOccLarge>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap) \
+                : launch_one(crop_mma_kernel<SRC, 1, kOccSmall>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap))
     if (src_f32) {
         if (W % 4 != 0 || ((uintptr_t)canvas & 15) != 0) {
             set_error("usdu_tile_crop_resize_f32: the image width must be a multiple of 4 and the image 16-byte aligned");
             return USDU_ERR_UNSUPPORTED;
         }
         const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, false);
-        return two_ksteps ? launch_one(crop_mma_kernel<2, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
-                          : launch_one(crop_mma_kernel<2, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+        return USDU_CROP_LAUNCH(2);
     }
     // TMA staging needs the patch to fit the two boxes (the planner keeps the staged rows <= 48 for scales <= ~1.2)
     bool use_tma = plane_rows <= kBoxR && 12 + patch_w * 3 <= 2 * kBoxB && ((uintptr_t)canvas & 15) == 0;
     if (use_tma) use_tma = tma::encode_u8_3d(&cmap, canvas, (uint64_t)W * 3, (uint64_t)H, (uint64_t)B, (uint64_t)pitch, kBoxB, kBoxR);
     const size_t smem = crop_smem(patch_w, plane_rows, mid_rows, use_tma);
-    if (use_tma)
-        return two_ksteps ? launch_one(crop_mma_kernel<1, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
-                          : launch_one(crop_mma_kernel<1, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
-    return two_ksteps ? launch_one(crop_mma_kernel<0, 2>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap)
-                      : launch_one(crop_mma_kernel<0, 1>, smem, grid, st, cv, H, pitch, tabs, items, out, patch_w, plane_rows, mid_rows, W3, cmap);
+    if (use_tma) return USDU_CROP_LAUNCH(1);
+    return USDU_CROP_LAUNCH(0);
+#undef USDU_CROP_LAUNCH
 }
 
 int launch_blend(uint8_t* canvas, int B, int H, int W, int64_t pitch, const int32_t* tabs, const uint8_t* mask_pool,
