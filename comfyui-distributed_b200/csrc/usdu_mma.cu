@@ -263,7 +263,7 @@ __device__ __forceinline__ int div_u16(int i, uint32_t m) { return m ? (int)__um
 // kU units per thread per trip, every load issued before the first use (12 x 16 bytes in flight per thread).
 __device__ __forceinline__ void stage_f32(uint8_t* planes, int PB, int plane_rows, const float* __restrict__ src, int64_t pitch_f,
                                           int rows, int cols) {
-    constexpr int kU = 3;
+    constexpr int kU = 4;                       // 1024 units per trip: a 128 x 16 block (<= 825 units) is staged in ONE round of loads
     const int chunks = cols >> 2, total = rows * chunks;
     const uint32_t rc = recip_u16(chunks);
     for (int i0 = threadIdx.x; i0 < total; i0 += kT * kU) {

@@ -2,7 +2,8 @@
 tools/one_step.py into profiles/<name>.json: DRAM traffic of the seam-blend (and crop) launches of ONE step, next to the
 algorithmic bytes, stamped with the hash of the kernel sources it was captured from (bench.py prints `roofline.traffic`
 only when that hash matches the sources it runs).
-usage: python tools/traffic_summary.py launches.csv out.json [workload]"""
+usage: python tools/traffic_summary.py launches.csv out.json [workload] [source-hash file written on the GPU box beside the
+capture: `python -c "import bench; print(bench.kernel_source_hash())" > hash.txt`]"""
 import csv
 import json
 import os
@@ -38,7 +39,8 @@ from comfyui_distributed_b200 import planner  # noqa: E402
 B, H, W, tile, pad, blur = bench.WORKLOADS[workload]
 plan = planner.get_plan(W, H, tile, tile, pad, blur, True)
 n_waves = len(plan.waves())
-res = {"workload": workload, "source_hash": bench.kernel_source_hash(), "launches_per_step": n_waves,
+src_hash = open(sys.argv[4]).read().strip() if len(sys.argv) > 4 else bench.kernel_source_hash()
+res = {"workload": workload, "source_hash": src_hash, "launches_per_step": n_waves,
        "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none on tools/one_step.py; "
               "the LAST launches_per_step launches of each kernel = the timed step (cold-cache, serialised: bytes are meaningful, times are not)"}
 for key, pat in (("blend", "blend_"), ("crop_resize", "crop_")):
