@@ -74,22 +74,24 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi, uint32_t upper) {
     return d;
 }
 
-// fragment section of a table (planner.build_mma_frags)
+// fragment section of a table (planner.build_mma_frags): {n_mt, ksteps, 0, 0} then per M-tile {k0, 0, 0, 0, fragments of
+// (k-step, limb): 32 lanes x 4 registers}.  Everything is addressed from (section, mt, KS): no dependent load in front of
+// the fragment loads.
 struct FragTable {
-    const int32_t* base;       // tabs + section
-    int n_mt, fbase;
-    __device__ __forceinline__ FragTable(const int32_t* tabs, int section) : base(tabs + section) {
-        n_mt = __ldg(base);
-        fbase = 4 + ((n_mt + 3) & ~3);
-    }
-    __device__ __forceinline__ int k0(int mt) const { return __ldg(base + 4 + mt); }
+    const int32_t* base;       // tabs + section + 4
+    __device__ __forceinline__ FragTable(const int32_t* tabs, int section) : base(tabs + section + 4) {}
+    template <int KS>
+    __device__ __forceinline__ const int32_t* tile(int mt) const { return base + (size_t)mt * (4 + KS * 384); }
+    template <int KS>
+    __device__ __forceinline__ int k0(int mt) const { return __ldg(tile<KS>(mt)); }
     template <int KS>
     __device__ __forceinline__ void load(uint32_t (&a)[KS][3][4], int mt, int lane) const {
+        const int4* f = reinterpret_cast<const int4*>(tile<KS>(mt) + 4);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
-                const int4 q = __ldg(reinterpret_cast<const int4*>(base + fbase) + ((mt * KS + ks) * 3 + l) * 32 + lane);
+                const int4 q = __ldg(f + (ks * 3 + l) * 32 + lane);
                 a[ks][l][0] = q.x; a[ks][l][1] = q.y; a[ks][l][2] = q.z; a[ks][l][3] = q.w;
             }
     }
@@ -155,7 +157,7 @@ __device__ __forceinline__ void hpass(const uint8_t* __restrict__ planes, uint32
     for (int mt = G.mt0 + w; mt <= G.mt1; mt += kT / 32) {
         uint32_t a[KS][3][4];
         F.load<KS>(a, mt, lane);
-        const int krel = F.k0(mt) - sx0;                       // >= 0, multiple of 4
+        const int krel = F.k0<KS>(mt) - sx0;                       // >= 0, multiple of 4
         uint32_t* mcol = mid + 3 * ((mt << 4) + g - G.o_org);
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
@@ -216,7 +218,7 @@ __device__ __forceinline__ void vpass(const uint32_t* __restrict__ mid, const in
         F.load<KS>(a, mv, lane);
         const int r0 = (mv << 4) + g - oyb;                     // block row of output m = g; m = g + 8 is r0 + 8
         epi.rows(r0, r0 + 8);
-        const uint32_t* mp = mid + (((F.k0(mv) - sy0) >> 2) + t) * MIDP + G.coff + g + 16 * w;
+        const uint32_t* mp = mid + (((F.k0<KS>(mv) - sy0) >> 2) + t) * MIDP + G.coff + g + 16 * w;
         int strip = 4 * w + sub;
 #pragma unroll 1
         for (int p = w; p < PAIRS; p += kT / 32, mp += 16 * (kT / 32), strip += 4 * (kT / 32)) {

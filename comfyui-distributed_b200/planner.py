@@ -120,7 +120,7 @@ def build_mma_frags(tab: np.ndarray) -> Optional[np.ndarray]:
     8-bit limbs, coef = l2 * 65536 + l1 * 256 + l0 (l0, l1 unsigned, l2 signed), one u8 x u8 / s8 x u8 IMMA each with
     exact s32 accumulation.  Outputs are grouped in M-tiles of 16 (aligned in OUTPUT index space); M-tile mt reads the
     inputs k0[mt] .. k0[mt] + 32 * ksteps (k0 a multiple of 4: the kernels read them with 32-bit shared-memory loads).
-    -> int32 words {n_mtiles, ksteps, 0, 0, k0[n_mtiles] (padded to x4), fragments}, fragments = for (mt, kstep, limb)
+    -> int32 words {n_mtiles, ksteps, 0, 0} then per M-tile {k0, 0, 0, 0, fragments}, fragments = for (kstep, limb)
     32 lanes x 4 registers in the A-operand layout of mma.m16n8k32 (lane = 4 g + t: a0 = A[g][4t..4t+3],
     a1 = A[g+8][4t..], a2 = A[g][16+4t..], a3 = A[g+8][16+4t..]), or None when an M-tile needs more than
     MMA_MAX_KSTEPS k-steps (extreme down-scales: those plans keep the integer-pipe kernels)."""
@@ -156,10 +156,18 @@ def build_mma_frags(tab: np.ndarray) -> Optional[np.ndarray]:
         regs.append(sel)
     R = np.stack(regs, 0)                                         # [reg, lane, byte, limb, mt, ks]
     R = np.transpose(R, (4, 5, 3, 1, 0, 2))                       # [mt, ks, limb, lane, reg, byte]
-    words = np.ascontiguousarray(R).view(np.uint32).reshape(-1).view(np.int32)
-    pad = (-n_mt) % 4
-    head = np.concatenate([np.array([n_mt, ksteps, 0, 0], np.int32), k0.astype(np.int32), np.zeros(pad, np.int32)])
-    return np.ascontiguousarray(np.concatenate([head, words]))
+    words = np.ascontiguousarray(R).view(np.uint32).reshape(n_mt, -1).view(np.int32)          # [mt, ksteps * 3 * 128]
+    # per M-tile: {k0, 0, 0, 0} then its fragments, so that a kernel that knows mt and ksteps (job record) addresses both
+    # without first loading anything from the section (no dependent load before the fragment loads)
+    per_mt = np.concatenate([np.stack([k0, np.zeros_like(k0), np.zeros_like(k0), np.zeros_like(k0)], 1).astype(np.int32), words], 1)
+    head = np.array([n_mt, ksteps, 0, 0], np.int32)
+    return np.ascontiguousarray(np.concatenate([head, per_mt.reshape(-1)]))
+
+
+def mma_frag_k0(frags: np.ndarray) -> np.ndarray:
+    """K-window starts per M-tile of a fragment section."""
+    n_mt, ks = int(frags[0]), int(frags[1])
+    return frags[4:].reshape(n_mt, 4 + ks * 384)[:, 0].astype(np.int64)
 
 
 # --------------------------------------------------------------------------------------
@@ -260,7 +268,7 @@ class Plan:
                     self.tabs = np.concatenate([self.tabs, np.zeros(pad, np.int32)])
                 n_mt = int(frags[0])
                 self._tab_frag[key], self._tab_ks[key] = foff, int(frags[1])
-                self._tab_k0[key] = frags[4:4 + n_mt].astype(np.int64)
+                self._tab_k0[key] = mma_frag_k0(frags)
                 self._tab_end[key] = (b[:, 0] + b[:, 1]).astype(np.int64)
             self._tab_first[key] = b[:, 0].astype(np.int64)
             self._tab_span[key] = np.stack([b[:, 0], b[:, 0] + np.maximum(b[:, 1], taps)], 1)   # [lo, hi) per output

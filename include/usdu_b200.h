@@ -190,7 +190,7 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
 /* USDU_FLAG_MMA selects the tensor-core kernels (usdu_mma.cu: every LANCZOS tap runs as mma.sync.m16n8k32 on 8-bit
  * coefficient limbs, bit-identical results).  items_dev then holds job records in the TENSOR-CORE flavour: the same 32
  * words, with USDU_J_ROWS_H / _V = table-pool index of the axis' fragment section (host side: planner.build_mma_frags;
- * {n_mtiles, ksteps, 0, 0, k0[n_mtiles] padded to x4, then per (M-tile, k-step, limb) 32 lanes x 4 registers}),
+ * {n_mtiles, ksteps, 0, 0} then per M-tile {k0, 0, 0, 0, per (k-step, limb) 32 lanes x 4 registers}),
  * USDU_J_TAPS_H / _V = k-steps (1 or 2), USDU_J_IX0 / _IY0 = first staged input column / row (multiples of 4),
  * USDU_J_COLS a multiple of 4, USDU_J_LEAD = 0, crop: USDU_J_SRC_A a multiple of 4 and USDU_J_CY1 = block rows (16 / 32).
  * patch_w = bytes a plane row must hold (staged pixels or the reach of the last K window, whichever is larger);

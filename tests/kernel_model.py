@@ -152,9 +152,9 @@ def _frag(tabs, section, mt):
     """-> (k0, A[16, 32 * ksteps] int64) of M-tile mt, rebuilt from the fragment registers."""
     n_mt, ks = int(tabs[section]), int(tabs[section + 1])
     assert 0 <= mt < n_mt, f"M-tile {mt} outside the table ({n_mt})"
-    k0 = int(tabs[section + 4 + mt])
-    fbase = section + 4 + ((n_mt + 3) & ~3)
-    w = tabs[fbase + mt * ks * 3 * 128: fbase + (mt + 1) * ks * 3 * 128].view(np.uint32).reshape(ks, 3, 32, 4)
+    tile = section + 4 + mt * (4 + ks * 384)                   # {k0, 0, 0, 0, fragments} per M-tile
+    k0 = int(tabs[tile])
+    w = tabs[tile + 4: tile + 4 + ks * 384].view(np.uint32).reshape(ks, 3, 32, 4)
     A = np.zeros((16, 32 * ks), dtype=np.int64)
     for s in range(ks):
         for limb in range(3):
