@@ -535,7 +535,10 @@ int usdu_quantize_rows(const float* img_dev, uint8_t* canvas_dev, int B, int H, 
     const int W3 = W * 3;
     const int vec_ok = (W3 % 4 == 0) && (((uintptr_t)img_dev & 15) == 0) && (((uintptr_t)canvas_dev & 15) == 0);
     const int64_t total = (int64_t)B * (y1 - y0) * ((W3 + 15) / 16);
-    const int grid = grid_for((total + kThreads - 1) / kThreads);
+    // short-lived CTAs (up to 148 x 128 of them, ~1 trip each on the 8K canvas): when this pass runs on a side stream beside
+    // small tile waves (engine.OverlappedJob) SM slots turn over every microsecond instead of being held for the whole pass
+    const int64_t qblocks = (total + kThreads - 1) / kThreads;
+    const int grid = (int)(qblocks < 1 ? 1 : (qblocks > 148 * 128 ? 148 * 128 : qblocks));
     quantize_canvas_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img_dev, canvas_dev, B * (y1 - y0), W3, pitch, vec_ok, H, y0, y1 - y0);
     USDU_CUDA(cudaGetLastError());
     return USDU_OK;
@@ -561,7 +564,7 @@ int usdu_dequantize_rows(const uint8_t* canvas_dev, float* img_dev, int B, int H
     if (gx < 1) gx = 1;
     int64_t gy = (int64_t)B * (y1 - y0);
     if (gy > 65535) gy = 65535;
-    if (gy * gx > 148 * 16) gy = (148 * 16 + gx - 1) / gx;
+    if (gy * gx > 148 * 128) gy = (148 * 128 + gx - 1) / gx;       // short-lived CTAs, see usdu_quantize_rows
     if (gy < 1) gy = 1;
     dequantize_canvas_kernel<<<dim3(gx, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(canvas_dev, img_dev, B * (y1 - y0), W3, pitch, vec_ok, H, y0, y1 - y0);
     USDU_CUDA(cudaGetLastError());

@@ -581,74 +581,6 @@ class GraphedWaves:
         return c
 
 
-OVERLAP_ENDS = os.environ.get("USDU_OVERLAP_ENDS", "1") != "0"
-
-
-class OverlappedJob:
-    """The 1-GPU job with its two whole-canvas passes hidden under the small waves at both ends.
-
-    Q0 (fp32 image -> u8 canvas) and the final dequantise are each a full pass over 0.5 GB at HBM speed (~80 us on the 8K
-    canvas) during which no tile runs, while the first and last quarter of the 31 waves are 1-4 tiles and leave most SMs
-    idle.  The wave loop is captured as THREE graphs (first quarter / middle / last quarter of the waves); only the rows
-    the first segment's windows reach are quantised up front, the rest on a side stream while the first segment runs; the
-    rows no tile of the last segment can touch any more are dequantised on a second side stream while the last segment
-    runs.  Same kernels, same order inside the dependency DAG: bit-identical (tests/test_gpu_fullsize.py)."""
-
-    _cache: Dict[tuple, "OverlappedJob"] = {}
-    MIN_WAVES = 12
-
-    @staticmethod
-    def eligible(plan: Plan) -> bool:
-        return OVERLAP_ENDS and len(plan.waves()) >= OverlappedJob.MIN_WAVES
-
-    def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, skip: Sequence[str]):
-        plan = dp.plan
-        self.dp, self.B = dp, B
-        waves = plan.waves()
-        q = max(len(waves) // 4, 1)
-        segs = [waves[:q], waves[q:len(waves) - q], waves[len(waves) - q:]]
-        orders = [[t for w in seg for t in w] for seg in segs]
-        self.canvas = Canvas(dp, B)
-        self.graphs = [GraphedWaves.get(dp, B, denoiser, None, order=o, skip=skip, canvas_buf=self.canvas.buf) for o in orders]
-        self.in_rows = min(max(plan.tiles[t].y2 for t in orders[0]), plan.H)           # what the first segment reads
-        self.fin_rows = max(min(plan.tiles[t].y1 + plan.support(plan.tiles[t])[1] for t in orders[2]), 0)   # final before the last one
-        self.s_q = torch.cuda.Stream(device=dp.device)
-        self.s_d = torch.cuda.Stream(device=dp.device)
-        self.launches = sum(g.launches_per_replay for g in self.graphs) + 4
-        self.algo_bytes = sum(g.bytes_per_replay for g in self.graphs)
-
-    @classmethod
-    def get(cls, dp: DevicePlan, B: int, denoiser: Denoiser, skip: Sequence[str] = ()) -> "OverlappedJob":
-        key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), tuple(skip), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE, FUSE_LEVELS)
-        job = cls._cache.get(key)
-        if job is None or job.dp is not dp:
-            if len(cls._cache) > 4:
-                cls._cache.clear()
-            job = cls._cache[key] = OverlappedJob(dp, B, denoiser, skip)
-        return job
-
-    def run(self, image: torch.Tensor) -> torch.Tensor:
-        p, c, B = self.dp.plan, self.canvas, self.B
-        main = torch.cuda.current_stream(self.dp.device)
-        image = image.contiguous()
-        out = torch.empty((B, p.H, p.W, 3), dtype=torch.float32, device=self.dp.device)
-        self.s_q.wait_stream(main)                       # the canvas and `out` are free (earlier work of this stream is done)
-        self.s_d.wait_stream(main)
-        nat.quantize_rows(image.data_ptr(), c.buf.data_ptr(), B, p.H, p.W, c.pitch, 0, self.in_rows, _stream_ptr())
-        with torch.cuda.stream(self.s_q):
-            nat.quantize_rows(image.data_ptr(), c.buf.data_ptr(), B, p.H, p.W, c.pitch, self.in_rows, p.H, _stream_ptr())
-        self.graphs[0].graph.replay()
-        main.wait_stream(self.s_q)
-        self.graphs[1].graph.replay()
-        self.s_d.wait_stream(main)
-        with torch.cuda.stream(self.s_d):
-            nat.dequantize_rows(c.buf.data_ptr(), out.data_ptr(), B, p.H, p.W, c.pitch, 0, self.fin_rows, _stream_ptr())
-        self.graphs[2].graph.replay()
-        nat.dequantize_rows(c.buf.data_ptr(), out.data_ptr(), B, p.H, p.W, c.pitch, self.fin_rows, p.H, _stream_ptr())
-        main.wait_stream(self.s_d)
-        return out
-
-
 def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, tile_height: int, padding: int,
                    mask_blur: int, force_uniform_tiles: bool = True, stats: Optional[dict] = None,
                    use_graph: Optional[bool] = None, _skip: Sequence[str] = ()) -> torch.Tensor:
@@ -661,14 +593,6 @@ def upscale_single(image: torch.Tensor, denoiser: Denoiser, tile_width: int, til
         use_graph = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
     with torch.cuda.device(image.device):
         dp = DevicePlan.get(plan, image.device)
-        if use_graph and PROFILE is None and OverlappedJob.eligible(plan):
-            job = OverlappedJob.get(dp, B, denoiser, _skip)
-            res = job.run(image)
-            if stats is not None:
-                stats["gpu_launches"] = stats.get("gpu_launches", 0) + job.launches
-                stats["algo_bytes"] = stats.get("algo_bytes", 0) + job.algo_bytes
-                stats["tiles"], stats["waves"] = len(plan.tiles), len(plan.waves())
-            return res
         if use_graph:
             canvas = GraphedWaves.get(dp, B, denoiser, PROFILE, skip=_skip).replay(image)
         else:
