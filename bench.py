@@ -438,6 +438,29 @@ def main():
                 parity["why"] = "planner.partition differs from the assignment the digest was generated for"
             ok = int(match)
         del out_dev, out_e2e
+        if world > 1:
+            # the other two multi-rank paths of SURVEY.md 8f, checked here so that every N-GPU bench run proves them:
+            # (f2) exact mode == the 1-GPU digest at this world size; (f1) the collector's order and quantisation asymmetry
+            exp1, _ = expected_digest("cfg1_512_256px", 1)
+            B1, H1, W1, t1, p1, b1 = WORKLOADS["cfg1_512_256px"]
+            img1 = make_canvas_cpu(B1, H1, W1).to(dev)
+            ex = udist.upscale_exact(img1, den, t1, t1, p1, b1, True)
+            from comfyui_distributed_b200.nodes import DistributedCollectorNode
+            g = torch.Generator().manual_seed(100 + rank)
+            mine = torch.rand(1 + rank % 2, 64, 48, 3, generator=g)
+            ids = [f"rank{r}" for r in range(1, world)]
+            got_c, _ = DistributedCollectorNode().run(mine, multi_job_id="bench", is_worker=rank != 0, enabled_worker_ids=json.dumps(ids),
+                                                      worker_id="" if rank == 0 else f"rank{rank}")
+            if rank == 0:
+                parts = [mine]
+                for r in range(1, world):
+                    w = torch.rand(1 + r % 2, 64, 48, 3, generator=torch.Generator().manual_seed(100 + r))
+                    parts.append((w * 255).to(torch.uint8).to(torch.float32) / 255)         # worker images travel as trunc(255 x)
+                parity["exact_mode_cfg1_equals_1gpu_digest"] = bool(exp1 is not None and result_digest(ex) == exp1["sha256"])
+                parity["collector_order_and_values"] = bool(torch.equal(got_c, torch.cat(parts, 0)))
+                ok = int(ok and parity["exact_mode_cfg1_equals_1gpu_digest"] and parity["collector_order_and_values"])
+                parity["match"] = bool(ok)
+            del ex
         flag = torch.tensor([ok], device=dev)
         if world > 1:
             td.broadcast(flag, 0)
