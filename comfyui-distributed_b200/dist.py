@@ -769,18 +769,20 @@ def gather_to_root(payload: torch.Tensor, extra: dict, group=None):
     flat = payload.contiguous().view(-1)
     if rank != 0:
         if flat.numel():
-            td.send(flat, dst=root, group=group)
+            for w in td.batch_isend_irecv([td.P2POp(td.isend, flat, root, group)]):
+                w.wait()
         return None, None
-    parts, reqs = [payload], []
+    parts, ops = [payload], []
     for r in range(1, world):
         shape = records[r]["shape"]
         buf = torch.empty(int(np.prod(shape)), dtype=torch.uint8, device=payload.device)
         if buf.numel():
             src = td.get_global_rank(group, r) if group is not None else r
-            reqs.append(td.irecv(buf, src=src, group=group))
+            ops.append(td.P2POp(td.irecv, buf, src, group))
         parts.append(buf.view(shape))
-    for q in reqs:
-        q.wait()
+    if ops:
+        for w in td.batch_isend_irecv(ops):       # one batched group of receives (no per-op serialisation on NCCL)
+            w.wait()
     return parts, records
 
 
