@@ -190,12 +190,12 @@ class StaticJob:
         self.where, sizes = tile_payload_layout(plan, proc, B)
         self.sizes = [max(sz, 16) for sz in sizes]
         pitch = Canvas.pitch_of(plan.W)
-        self.canvas_bytes = B * plan.H * pitch
+        self.canvas_bytes = B * plan.H * pitch          # (symmetric allocations below are rounded up: slack behind the last row)
         self.peer = PeerPayload.get((max(self.sizes) + 255) // 256 * 256, device, group) if world > 1 else None
         self.work = self.final = None
         if self.peer is not None and USE_SHARED_FINAL_BLEND:
-            self.work = PeerPayload.get(self.canvas_bytes, device, group, tag="work")
-            self.final = PeerPayload.get(self.canvas_bytes, device, group, tag="final")
+            self.work = PeerPayload.get(self.canvas_bytes + 256, device, group, tag="work")
+            self.final = PeerPayload.get(self.canvas_bytes + 256, device, group, tag="final")
         self.sharded = self.final is not None and self.work is not None
         if world > 1:
             self.payload = (self.peer.buf[: self.sizes[self.rank]] if self.peer is not None

@@ -158,7 +158,10 @@ class Canvas:
         self.B = B
         self.pitch = self.pitch_of(self.plan.W)
         if buf is None:
-            buf = torch.empty((B, self.plan.H, self.pitch), dtype=torch.uint8, device=dplan.device)
+            # 16 bytes of slack behind the last row: the LDG staging of the integer-pipe kernels reads whole 12-byte chunks
+            # and, for widths that are not multiples of 4, may touch up to 4 bytes past the last row's pitch (discarded)
+            n = B * self.plan.H * self.pitch
+            buf = torch.empty(n + 16, dtype=torch.uint8, device=dplan.device)[:n].view(B, self.plan.H, self.pitch)
         elif tuple(buf.shape) != (B, self.plan.H, self.pitch) or buf.dtype != torch.uint8 or not buf.is_contiguous():
             raise ValueError(f"canvas buffer must be contiguous uint8 [{B},{self.plan.H},{self.pitch}]")
         self.buf = buf                      # caller-owned when given (dist.py: symmetric memory peers can address)
