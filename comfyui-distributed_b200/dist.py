@@ -269,7 +269,7 @@ class StaticJob:
         run_progressive(canvas, self.asg[self.rank], denoiser, payload=self.payload, where=self.where, skip=self.skip)
         return canvas
 
-    def composite_slab(self, image_ptr: int, frame_stride_rows: Optional[int] = None):
+    def composite_slab(self, image_ptr: int):
         """Phase B: this rank's slab of the final canvas = quantised input rows + every tile, in the reference's order.
         image_ptr: address of row 0 of frame 0 of the fp32 input as THIS process sees it (a slab upload passes an
         address offset so that its first row lands on the slab's first row)."""
