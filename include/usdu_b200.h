@@ -208,10 +208,11 @@ int usdu_box_blur_params(float radius, int32_t* rad, uint32_t* ww, uint32_t* fw)
  * bits 8..15 (<= USDU_BLOCK_H), columns in bits 16..23 (<= USDU_BLOCK_W); 0 = the default block.
  * The planner shrinks blocks when an extreme down-scale would not fit shared memory. */
 #define USDU_FLAG_BLOCK_COLS(n) ((n) << 16)
-/* usdu_tile_blend: canvas_dev is ANOTHER device's memory mapped into this process (NVLink peer
- * access); the kernel then waits for its bulk stores to complete, not only to be read, and issues
- * a system-scope fence before a CTA exits (the multi-GPU final blend composites shares of the
- * master's canvas from every rank, dist.upscale_static). */
+/* usdu_tile_blend (integer-pipe kernels): canvas_dev is ANOTHER device's memory mapped into this process (NVLink peer
+ * access); the kernel then waits for its bulk stores to complete, not only to be read, and issues a system-scope fence
+ * before a CTA exits.  Round 1's multi-GPU final blend stored into the master's canvas this way; since round 2 every rank
+ * composites a slab of the final canvas in its OWN memory and the master gathers the slabs with peer loads
+ * (usdu_gather_dequantize), so nothing in the package sets this flag any more. */
 #define USDU_FLAG_REMOTE_CANVAS (1 << 24)
 /* Q0: canvas_u8[b][y][x*3+c] = (uint8)(255.f * img[b][y][x][c])   (utils/image.py:8-10)
  * pitch = bytes per canvas row (>= 3*W, multiple of 16); frame stride = H*pitch. */
