@@ -24,6 +24,8 @@ import numpy as np
 import torch
 import torch.distributed as td
 
+from .lru import LruCache
+
 
 def dist_info(group=None) -> Tuple[int, int]:
     if td.is_available() and td.is_initialized():
@@ -104,7 +106,7 @@ def peer_offsets(order: Sequence[int], where: Dict[int, Tuple[int, int]], ptrs: 
 class PeerPayload:
     """Symmetric u8 buffer + rendezvous handle, cached per (tag, bytes, device, group)."""
 
-    _cache: Dict[tuple, Optional["PeerPayload"]] = {}
+    _cache: "LruCache[Optional[PeerPayload]]" = LruCache(8)
     _warned = False
 
     def __init__(self, nbytes: int, device, group):
@@ -132,7 +134,7 @@ class PeerPayload:
             return None
         key = (tag, int(nbytes), str(device), id(group))
         if key in cls._cache:
-            return cls._cache[key]
+            return cls._cache.get(key)
         obj, ok = None, 1
         try:
             obj = PeerPayload(int(nbytes), device, group)
@@ -149,10 +151,7 @@ class PeerPayload:
                 warnings.warn("comfyui-distributed_b200: symmetric-memory peer transport unavailable "
                               f"({cls.last_error or 'a peer rank failed'}); falling back to NCCL all_gather of the tiles",
                               RuntimeWarning, stacklevel=2)
-        if len(cls._cache) > 8:
-            cls._cache.clear()
-        cls._cache[key] = obj
-        return obj
+        return cls._cache.put(key, obj)
 
     last_error: Optional[str] = None
 
@@ -171,7 +170,7 @@ class StaticJob:
     buffers (u8 tile payload, working canvas, final canvas), the captured per-rank wave graph and the slab of the
     final canvas this rank composites.  Cached: a second job of the same shape only replays."""
 
-    _cache: Dict[tuple, "StaticJob"] = {}
+    _cache: "LruCache[StaticJob]" = LruCache(4)
 
     def __init__(self, plan, B: int, device, group, denoiser, assignment, graphed: bool):
         from . import engine as _eng
@@ -235,12 +234,8 @@ class StaticJob:
         akey = None if assignment is None else tuple(tuple(a) for a in assignment)
         key = (id(plan), B, str(device), id(group), getattr(denoiser, "graph_key", id(denoiser)) if graphed else "eager",
                akey, graphed, _eng.FORCE_GENERIC, _eng.FORCE_NO_MMA, USE_PEER_BLEND, USE_SHARED_FINAL_BLEND)
-        job = cls._cache.get(key)
-        if job is None or job.plan is not plan:
-            if len(cls._cache) > 4:
-                cls._cache.clear()
-            job = cls._cache[key] = StaticJob(plan, B, device, group, denoiser, assignment, graphed)
-        return job
+        return cls._cache.get_or_build(key, lambda: StaticJob(plan, B, device, group, denoiser, assignment, graphed),
+                                       lambda job: job.plan is plan)
 
     # ---- phases -----------------------------------------------------------------------------
     def run_tiles(self, image: Optional[torch.Tensor], denoiser, resident: bool = False):
@@ -638,17 +633,13 @@ def upscale_static_host(host_image: torch.Tensor, denoiser, tile_width: int, til
     return out if rank == 0 else None
 
 
-_PAYLOADS: Dict[tuple, torch.Tensor] = {}
+_PAYLOADS: "LruCache[torch.Tensor]" = LruCache(8)
 
 
 def _payload_buffer(nbytes: int, device) -> torch.Tensor:
     """Reused send buffer of the NCCL transport (stable address: it is baked into the wave graph)."""
     key = (int(nbytes), str(device))
-    if key not in _PAYLOADS:
-        if len(_PAYLOADS) > 8:
-            _PAYLOADS.clear()
-        _PAYLOADS[key] = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
-    return _PAYLOADS[key]
+    return _PAYLOADS.get_or_build(key, lambda: torch.zeros(int(nbytes), dtype=torch.uint8, device=device))
 
 
 class ExactJob:
@@ -656,7 +647,7 @@ class ExactJob:
     layout, the send buffer and the gathered buffer (all sizes follow from the plan: no size exchange, no host sync,
     nothing allocated per job)."""
 
-    _cache: Dict[tuple, "ExactJob"] = {}
+    _cache: "LruCache[ExactJob]" = LruCache(4)
 
     def __init__(self, plan, B: int, device, group):
         from .engine import _sorted_by_shape
@@ -676,12 +667,7 @@ class ExactJob:
     @classmethod
     def get(cls, plan, B, device, group) -> "ExactJob":
         key = (id(plan), B, str(device), id(group))
-        job = cls._cache.get(key)
-        if job is None or job.plan is not plan:
-            if len(cls._cache) > 4:
-                cls._cache.clear()
-            job = cls._cache[key] = ExactJob(plan, B, device, group)
-        return job
+        return cls._cache.get_or_build(key, lambda: ExactJob(plan, B, device, group), lambda job: job.plan is plan)
 
 
 def upscale_exact(image: torch.Tensor, denoiser, tile_width: int, tile_height: int, padding: int, mask_blur: int,

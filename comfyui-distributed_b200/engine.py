@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from .lru import LruCache
 from .planner import Plan, Tile, WorkList, get_plan
 
 Denoiser = Callable[[torch.Tensor, List[Tile]], torch.Tensor]
@@ -92,7 +93,7 @@ def _launch(name: str, nbytes: int, fn):
 class DevicePlan:
     """Plan tables resident on one device (+ the feather templates, built there)."""
 
-    _cache: Dict[tuple, "DevicePlan"] = {}
+    _cache: "LruCache[DevicePlan]" = LruCache(8)
 
     def __init__(self, plan: Plan, device: torch.device):
         self.plan = plan
@@ -109,12 +110,7 @@ class DevicePlan:
     @classmethod
     def get(cls, plan: Plan, device: torch.device) -> "DevicePlan":
         key = (id(plan), device.index)
-        dp = cls._cache.get(key)
-        if dp is None or dp.plan is not plan:
-            if len(cls._cache) > 8:
-                cls._cache.clear()
-            dp = cls._cache[key] = DevicePlan(plan, device)
-        return dp
+        return cls._cache.get_or_build(key, lambda: DevicePlan(plan, device), lambda dp: dp.plan is plan)
 
     def _upload(self, wl: WorkList):
         items = torch.from_numpy(wl.items).to(self.device)
@@ -485,7 +481,7 @@ class GraphedWaves:
     wave, which removes the host enqueue gaps that dominate when the sampler is cheap.
     Only for samplers that declare `cuda_graph_safe` (pure device work, fixed shapes)."""
 
-    _cache: Dict[tuple, "GraphedWaves"] = {}
+    _cache: "LruCache[GraphedWaves]" = LruCache(6)
 
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, profile: Optional[KernelProfile],
                  order: Optional[Sequence[int]] = None, keep_processed: bool = False,
@@ -551,13 +547,9 @@ class GraphedWaves:
         ckey = None if canvas_buf is None else canvas_buf.data_ptr()
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)), id(profile), FORCE_GENERIC, FORCE_NO_MMA, SCHEDULE, FUSE_LEVELS,
                None if order is None else tuple(order), keep_processed, pkey, tuple(skip), ckey, external_crop)
-        gw = cls._cache.get(key)
-        if gw is None or gw.canvas.dp is not dp:
-            if len(cls._cache) > 6:
-                cls._cache.clear()
-            gw = cls._cache[key] = GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip,
-                                                canvas_buf, external_crop)
-        return gw
+        return cls._cache.get_or_build(
+            key, lambda: GraphedWaves(dp, B, denoiser, profile, order, keep_processed, payload, where, skip, canvas_buf,
+                                      external_crop), lambda gw: gw.canvas.dp is dp)
 
     def replay(self, image: torch.Tensor) -> Canvas:
         """Q0 from the caller's tensor (eager), then the captured wave loop."""
@@ -649,7 +641,7 @@ class HostPipeline:
     every canvas row above the next band's first writable row is final and can travel back
     while later bands are still uploading.  Three streams: upload, compute, download."""
 
-    _cache: Dict[tuple, "HostPipeline"] = {}
+    _cache: "LruCache[HostPipeline]" = LruCache(3)
 
     def __init__(self, dp: DevicePlan, B: int, denoiser: Denoiser, n_bands: int):
         plan = dp.plan
@@ -670,11 +662,7 @@ class HostPipeline:
         graph_safe = bool(getattr(denoiser, "cuda_graph_safe", False)) and USE_CUDA_GRAPHS
         # a captured pipeline belongs to one sampler configuration; an eager one serves any sampler
         key = (id(dp), B, getattr(denoiser, "graph_key", id(denoiser)) if graph_safe else "eager", n_bands, FORCE_GENERIC, FORCE_NO_MMA)
-        hp = cls._cache.get(key)
-        if hp is None or hp.dp is not dp:
-            if len(cls._cache) > 2:
-                cls._cache.clear()
-            hp = cls._cache[key] = HostPipeline(dp, B, denoiser, n_bands)
+        hp = cls._cache.get_or_build(key, lambda: HostPipeline(dp, B, denoiser, n_bands), lambda hp: hp.dp is dp)
         if not hp.graph_safe:
             hp.denoiser = denoiser
         return hp

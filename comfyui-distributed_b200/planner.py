@@ -21,6 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native as nat
+from .lru import LruCache
 
 
 # --------------------------------------------------------------------------------------
@@ -899,13 +900,9 @@ class Plan:
         return out
 
 
-_PLAN_CACHE: Dict[tuple, Plan] = {}
+_PLAN_CACHE: LruCache[Plan] = LruCache(16)
 
 
 def get_plan(W: int, H: int, tile_width: int, tile_height: int, padding: int, mask_blur: int, uniform: bool) -> Plan:
     key = (W, H, tile_width, tile_height, padding, mask_blur, bool(uniform))
-    if key not in _PLAN_CACHE:
-        if len(_PLAN_CACHE) > 16:
-            _PLAN_CACHE.clear()
-        _PLAN_CACHE[key] = Plan.build(*key)
-    return _PLAN_CACHE[key]
+    return _PLAN_CACHE.get_or_build(key, lambda: Plan.build(*key))

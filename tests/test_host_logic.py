@@ -389,3 +389,29 @@ def test_tile_dag_is_a_valid_parallel_schedule_of_the_progressive_order(W, H, ti
                 assert j in pred[i], (i, j)
     assert max(depth) + 1 >= len(p.waves())     # never shallower than the true dependency depth ...
     assert max(depth) + 1 <= len(p.waves()) + 2  # ... and no long false chains
+
+
+def test_caches_evict_the_least_recently_used_entry_only():
+    """Alternating geometries keep their plans (and, on the device, tables and graphs) warm: the host caches are LRU,
+    they never drop everything at once."""
+    from comfyui_distributed_b200.lru import LruCache
+    c = LruCache(3)
+    built = []
+
+    def make(k):
+        return c.get_or_build(k, lambda: built.append(k) or ("v", k))
+
+    for k in (1, 2, 3, 1, 4):                      # 4 evicts 2 (1 was touched after it)
+        make(k)
+    assert built == [1, 2, 3, 4] and list(c.keys()) == [3, 1, 4]
+    make(1), make(3)
+    assert built == [1, 2, 3, 4]
+    make(2)                                        # evicts 4, the least recently used
+    assert list(c.keys()) == [1, 3, 2] and len(c) == 3
+    # an id()-keyed entry whose object was replaced is rebuilt in place
+    assert c.get_or_build(2, lambda: "fresh", valid=lambda v: False) == "fresh" and len(c) == 3
+    # the plan cache: two alternating geometries never rebuild
+    a = planner.get_plan(640, 480, 128, 128, 16, 8, True)
+    for i in range(40):
+        planner.get_plan(300 + i, 200, 64, 64, 8, 4, True)
+        assert planner.get_plan(640, 480, 128, 128, 16, 8, True) is a
