@@ -416,10 +416,16 @@ class SharedHost:
     """Result buffers in POSIX shared memory, page-locked (cudaHostRegister) in every rank's process, plus a small
     control block for host-side hand-shakes.  The reference's workers each hold the whole canvas and the master alone
     returns the result (upscale/modes/static.py:209-212, :556-564); here every rank downloads its slab of the final
-    canvas into the master's result tensor directly, so no result byte crosses NVLink or the master's PCIe link."""
+    canvas into the master's result tensor directly, so no result byte crosses NVLink or the master's PCIe link.
+
+    Life time of the memory: a buffer's file is unlinked as soon as every rank has mapped it (a crashed job leaves nothing
+    in /dev/shm); at most MAX_MAPPED buffers stay mapped and page-locked -- when a new one is needed beyond that, rank 0
+    names the least recently used buffer its consumer has dropped and every rank unmaps it in the same hand-shake."""
 
     _inst: Dict[int, "SharedHost"] = {}
-    CTRL_WORDS = 64 + 64          # [0] job id published by rank 0, [1] buffer index of that job, [64 + r] last job rank r finished
+    CTRL_WORDS = 64 + 64          # [0] job id published by rank 0, [1] buffer index of that job, [2], [3] buffer (numel, index)
+    #                               every rank unmaps first ([3] < 0: none), [64 + r] last job rank r finished
+    MAX_MAPPED = 6
 
     def __init__(self, group):
         import atexit
@@ -430,15 +436,19 @@ class SharedHost:
         td.broadcast_object_list(tok, src=td.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.uid = tok[0]
         self.paths: List[str] = []
+        self.pin = torch.cuda.is_available()                # (the gloo tests drive the hand-shakes without a device)
         path = self._path("ctrl")
         if self.rank == 0:
             np.zeros(self.CTRL_WORDS, dtype=np.int64).tofile(path)
             self.paths.append(path)
+        atexit.register(self.close)
         td.barrier(group=group)
         self.ctrl = np.memmap(path, dtype=np.int64, mode="r+", shape=(self.CTRL_WORDS,))
+        td.barrier(group=group)
+        self._unlink(path)                                  # the mappings keep the memory alive
         self.job = 0
-        self.bufs: Dict[tuple, List[torch.Tensor]] = {}     # (nbytes) -> mapped + registered tensors by index
-        atexit.register(self.close)
+        self.bufs: Dict[int, List[Optional[torch.Tensor]]] = {}     # numel -> mapped + registered tensors by index
+        self.last_use: Dict[Tuple[int, int], int] = {}               # (numel, index) -> job
 
     @classmethod
     def get(cls, group) -> "SharedHost":
@@ -450,18 +460,26 @@ class SharedHost:
     def _path(self, name: str) -> str:
         return f"/dev/shm/usdu_b200_{self.uid}_{name}"
 
-    def close(self):
-        for p in self.paths:
+    def _unlink(self, path: str):
+        if self.rank == 0:
             try:
-                os.unlink(p)
+                os.unlink(path)
             except OSError:
                 pass
-        self.paths = []
+            if path in self.paths:
+                self.paths.remove(path)
+
+    def close(self):
+        for p in list(self.paths):
+            self._unlink(p)
+
+    def mapped(self) -> int:
+        return sum(1 for lst in self.bufs.values() for i in range(len(lst)) if lst[i] is not None)
 
     def _map(self, numel: int, k: int, touch: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-        """Buffer k of `numel` floats: mapped and page-locked on first use (~150 ms for 400 MB, once).  touch = (a, b):
-        element range this rank will write -- it is first-touched here, COLLECTIVELY (every rank maps a new buffer in the
-        same job, see begin())."""
+        """Buffer k of `numel` floats: mapped and page-locked on first use (~150 ms for 400 MB, once), COLLECTIVELY (every
+        rank maps a new buffer in the same job, see begin()).  touch = (a, b): element range this rank will write -- it
+        is first-touched here."""
         lst = self.bufs.setdefault(numel, [])
         while len(lst) <= k:
             lst.append(None)
@@ -476,12 +494,32 @@ class SharedHost:
                 a, b = touch
                 with _near_gpu_cpus():
                     t.view(-1)[a:b].zero_()
-                td.barrier(group=self.group)
-            err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * 4, 0)
-            if int(err) != 0:
-                raise RuntimeError(f"cudaHostRegister of the shared result buffer failed: {err}")
+            td.barrier(group=self.group)                    # everybody has the file open and mapped
+            self._unlink(path)
+            if self.pin:
+                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel * 4, 0)
+                if int(err) != 0:
+                    raise RuntimeError(f"cudaHostRegister of the shared result buffer failed: {err}")
             lst[k] = t
         return lst[k]
+
+    def _unmap(self, numel: int, k: int):
+        """Drop buffer (numel, k): nothing on this rank references it any more (rank 0 checked its consumer; the other
+        ranks only ever hold it inside one call, and synchronised their copies before finish())."""
+        lst = self.bufs.get(numel, [])
+        if k < len(lst) and lst[k] is not None:
+            if self.pin:
+                torch.cuda.cudart().cudaHostUnregister(lst[k].data_ptr())
+            lst[k] = None                                   # the last reference: the mapping goes with the storage
+        self.last_use.pop((numel, k), None)
+
+    def _pick_victim(self) -> Tuple[int, int]:
+        """Rank 0: the least recently used mapped buffer nobody references, or (0, -1)."""
+        from .engine import buffer_is_unreferenced
+        for (numel, k), _ in sorted(self.last_use.items(), key=lambda kv: kv[1]):
+            if self.bufs[numel][k] is not None and buffer_is_unreferenced(self.bufs[numel][k]):
+                return numel, k
+        return 0, -1
 
     def _wait(self, idx: int, value: int, what: str):
         import time
@@ -499,24 +537,33 @@ class SharedHost:
         self.job += 1
         if self.rank == 0:
             lst = self.bufs.setdefault(numel, [])
-            have = len(lst)
-            k = have                           # (index loop: a loop variable bound to the tensor would count as a reference)
-            for i in range(have):
+            k = -1                             # (index loops: a loop variable bound to the tensor would count as a reference)
+            for i in range(len(lst)):
                 if lst[i] is not None and buffer_is_unreferenced(lst[i]):
                     k = i
                     break
-            if k < have and torch.cuda.is_available():
-                torch.cuda.synchronize()       # copies a consumer may have queued out of a recycled buffer
-            if k >= have:                      # a new buffer: create the file, then publish, then map it together with the others
+            victim = (0, -1)
+            if k >= 0:
+                if self.pin:
+                    torch.cuda.synchronize()   # copies a consumer may have queued out of a recycled buffer
+            else:                              # a new buffer: create the file, then publish, then map it together with the others
+                k = next((i for i in range(len(lst)) if lst[i] is None), len(lst))
+                if self.mapped() >= self.MAX_MAPPED:
+                    victim = self._pick_victim()
                 with open(self._path(f"{numel}_{k}"), "wb") as f:
                     f.truncate(numel * 4)
                 self.paths.append(self._path(f"{numel}_{k}"))
             self.ctrl[1] = k
+            self.ctrl[2], self.ctrl[3] = victim
             self.ctrl[0] = self.job
         else:
             self._wait(0, self.job, "the master to publish the job")
             k = int(self.ctrl[1])
+            victim = (int(self.ctrl[2]), int(self.ctrl[3]))
+        if victim[1] >= 0:
+            self._unmap(*victim)
         buf = self._map(numel, k, touch)
+        self.last_use[(numel, k)] = self.job
         return buf.view(tuple(shape))
 
     def finish(self):

@@ -132,7 +132,6 @@ class DevicePlan:
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
-
     def level_list(self, blend_ids: Tuple[int, ...], offs: np.ndarray, crop_ids: Tuple[int, ...], B: int, share: int = 1):
         key = ("level", blend_ids, tuple(int(o) for o in offs), crop_ids, B, share)
         if key not in self._wl:
@@ -168,8 +167,8 @@ class Canvas:
         # integer-pipe build otherwise; both give identical bytes
         self.path_crop = min(self.path, PATH_CROP)
         self.path_blend = min(self.path, PATH_BLEND)
-        self.share = 1
-        self._sync = None                   # ticket + per-tile counters of the fused level launches (left at zero by the kernel)                      # launches expected to run side by side (tile-granular schedule)
+        self.share = 1                      # launches expected to run side by side (tile-granular schedule)
+        self._sync = None                   # ticket + per-tile counters of the fused level launches (left at zero by the kernel)
 
     @staticmethod
     def pitch_of(W: int) -> int:
@@ -757,15 +756,16 @@ class _PinnedPool:
     host allocator does not hand a block back quickly enough when the previous result is still
     referenced.  A buffer is recycled only if nothing but the pool references it: no other Python
     reference to the tensor object (views hold one through `_base`) and no other owner of its storage
-    (numpy arrays made with `.numpy()` and views own the storage without referencing the tensor)."""
+    (numpy arrays made with `.numpy()` and views own the storage without referencing the tensor).
+    Bounded: `keep` buffers per shape, `shapes` most recently used shapes (the rest goes back to torch's host allocator)."""
 
-    def __init__(self, keep: int = 3):
-        self.bufs: Dict[tuple, list] = {}
+    def __init__(self, keep: int = 3, shapes: int = 4):
+        self.bufs: "LruCache[list]" = LruCache(shapes)
         self.keep = keep
 
     def get(self, shape, dtype=torch.float32) -> torch.Tensor:
         key = (tuple(shape), dtype)
-        lst = self.bufs.setdefault(key, [])
+        lst = self.bufs.get_or_build(key, list)
         for i in range(len(lst)):
             if buffer_is_unreferenced(lst[i]):
                 # a consumer may have queued an asynchronous copy out of the buffer on some stream and dropped the

@@ -12,7 +12,6 @@ from __future__ import annotations
 import json
 
 import torch
-import torch.distributed as td
 
 from .. import dist as usdu_dist
 

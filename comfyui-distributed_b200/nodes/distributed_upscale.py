@@ -8,11 +8,16 @@ What changes behind the signature:
   injected by the reference's orchestrator (multi_job_id, is_worker, master_url,
   enabled_worker_ids, worker_id, tile_indices, dynamic_threshold) are accepted and
   validated the same way, but the role comes from the rank (rank 0 = master);
-* the tile pull-queue becomes a static plan (planner.partition).
+* the tile pull-queue becomes a static plan (planner.partition);
+* `semantics` (class / instance attribute, default from USDU_SEMANTICS, not a widget -- the signature stays the
+  reference's): "static" = the reference's multi-worker result for that plan (upscale/modes/static.py); "exact" = the
+  N ranks cooperatively compute the reference's SINGLE-GPU result (single_gpu.py:8-72), bit-identical at any world size
+  (dist.upscale_exact).
 """
 from __future__ import annotations
 
 import json
+import os
 
 import torch
 
@@ -65,6 +70,7 @@ class UltimateSDUpscaleDistributed:
     RETURN_TYPES = ("IMAGE",)
     FUNCTION = "run"
     CATEGORY = "image/upscaling"
+    semantics = os.environ.get("USDU_SEMANTICS", "static")       # multi-GPU jobs: "static" | "exact" (see module docstring)
 
     @classmethod
     def IS_CHANGED(cls, **kwargs):
@@ -116,6 +122,9 @@ class UltimateSDUpscaleDistributed:
                           "not supported; launch one rank per GPU with torch.distributed instead. Returning the input.",
                           RuntimeWarning, stacklevel=2)
             return (upscaled_image,)
+        if self.semantics not in ("static", "exact"):
+            raise ValueError(f"semantics must be 'static' or 'exact', got {self.semantics!r}")
+        exact = distributed and self.semantics == "exact"
         if not upscaled_image.is_cuda and not distributed:
             # ComfyUI IMAGE tensors live on the host: upload, kernels and download overlap band by band
             _, H, W, _ = upscaled_image.shape
@@ -123,7 +132,7 @@ class UltimateSDUpscaleDistributed:
                                            denoise, tiled_decode, (W, H))
             return (upscale_host(upscaled_image, denoiser, tile_width, tile_height, padding, mask_blur,
                                  force_uniform_tiles, device=dev, stats=self.last_stats),)
-        if distributed and not upscaled_image.is_cuda:
+        if distributed and not exact and not upscaled_image.is_cuda:
             # every rank moves only its slab of the image over its own PCIe link (dist.upscale_static_host)
             _, H, W, _ = upscaled_image.shape
             denoiser = self._make_denoiser(model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler,
@@ -143,8 +152,8 @@ class UltimateSDUpscaleDistributed:
         denoiser = self._make_denoiser(model, positive, negative, vae, seed, steps, cfg, sampler_name, scheduler,
                                        denoise, tiled_decode, (W, H))
         if distributed:
-            out = usdu_dist.upscale_static(image, denoiser, tile_width, tile_height, padding, mask_blur,
-                                           force_uniform_tiles, stats=self.last_stats)
+            run = usdu_dist.upscale_exact if exact else usdu_dist.upscale_static
+            out = run(image, denoiser, tile_width, tile_height, padding, mask_blur, force_uniform_tiles, stats=self.last_stats)
             if worker:
                 return (upscaled_image,)           # workers return their input (static.py:314)
         else:

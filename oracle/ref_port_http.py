@@ -32,7 +32,6 @@ import threading
 import time
 from typing import Dict, List
 
-import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))

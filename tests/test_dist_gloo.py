@@ -176,3 +176,36 @@ def test_peer_offsets_address_every_owner_buffer():
     assert list(offs) == [0x40000000, 0x7E0000000000 - 0x7F0000000000 + 16, 0x40000000 + 4096]
     assert list(udist.peer_offsets([0, 4], where, ptrs, own_rank=0)) == [0, 2048]
     assert list(udist.peer_offsets([1], where, ptrs, own_rank=1)) == [0]
+
+
+def _w_shared_host(rank, world):
+    import glob
+    sh = udist.SharedHost.get(None)
+    sh.MAX_MAPPED = 3
+    assert not sh.pin                                     # no device here: the hand-shakes and the mapping policy only
+    held = None
+    rows = [100, 200, 100, 300, 400, 500, 100, 200]
+    for j, n in enumerate(rows):
+        out = sh.begin((1, n, 4, 3), touch=(rank * (n // 2) * 12, (rank + 1) * (n // 2) * 12))
+        out[0, rank * (n // 2):(rank + 1) * (n // 2)] = 10 * j + rank     # this rank's slab
+        sh.finish()
+        if rank == 0:
+            assert torch.equal(out[0, :n // 2], torch.full((n // 2, 4, 3), 10.0 * j))
+            assert torch.equal(out[0, n // 2:], torch.full((n // 2, 4, 3), 10.0 * j + 1))
+            if j == 1:
+                held = out                                # a consumer that keeps its result: never recycled, never unmapped
+        assert sh.mapped() <= 3, (j, sh.mapped())
+        if j == 2:
+            assert sh.mapped() == 2                       # the dropped 100-row buffer was recycled, not mapped again
+        del out
+        td.barrier()
+        assert glob.glob(f"/dev/shm/usdu_b200_{sh.uid}_*") == []          # rank 0 unlinked it once everybody had mapped it
+        td.barrier()                                                      # (rank 0 creates the next job's file after this)
+    if rank == 0:
+        assert torch.equal(held[0, 100:], torch.full((100, 4, 3), 11.0))
+        assert sh.bufs[200 * 12][0] is not None and sh.bufs[200 * 12][1] is not None     # the second 200-row job got its own buffer
+    assert sorted(k for k in sh.last_use) == sorted((n, i) for n, lst in sh.bufs.items() for i in range(len(lst)) if lst[i] is not None)
+
+
+def test_shared_host_buffers_are_bounded_unlinked_and_never_taken_from_a_consumer():
+    _run(_w_shared_host, 2)

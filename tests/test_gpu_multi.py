@@ -218,6 +218,16 @@ def _w_node(rank, world):
         assert not out.is_cuda and np.array_equal(out.numpy(), ref)
     else:
         assert out is x
+    # semantics = "exact": the same call gives the SINGLE-GPU result, on host and device tensors
+    node.semantics = "exact"
+    single = orc.process_single(img, orc.make_t0_denoiser(9, 0.5), 128, 128, 16, 8, True)
+    for xx in (x, x.cuda()):
+        (out,) = node.run(xx, T0Model(), None, None, None, 9, 20, 8.0, "euler", "normal", 0.5, 128, 128, 16, 8, True, False,
+                          multi_job_id="job", is_worker=rank != 0, enabled_worker_ids='["w1"]', worker_id="" if rank == 0 else "w1")
+        if rank == 0:
+            assert out.is_cuda == xx.is_cuda and np.array_equal(out.cpu().numpy(), single)
+        else:
+            assert out is xx
     # collector: rank r contributes r+1 images
     g = torch.Generator().manual_seed(50 + rank)
     imgs = torch.rand(1 + rank, 40, 56, 3, generator=g)

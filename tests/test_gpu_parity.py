@@ -183,6 +183,38 @@ def test_node_accepts_host_tensor_and_returns_host_tensor():
     assert node.last_stats["gpu_launches"] > 0
 
 
+def test_alternating_geometries_keep_their_graphs_and_evict_one_at_a_time(kernel_path):
+    """Two jobs of different geometry called in turn replay their captured graphs (no recapture), and filling the graph
+    cache with other geometries evicts the least recently used entry only; results stay those of the reference."""
+    if kernel_path != "mma":
+        pytest.skip("host-side caching is the same for every kernel family")
+    cases = [c for c in SINGLE if c["B"] == 1][:2]
+    assert len(cases) == 2
+
+    def run(c):
+        img = torch.from_numpy(make_input(c["kind"], c["seed"], c["B"], c["H"], c["W"])).to(DEV)
+        out = engine.upscale_single(img, T0Denoiser(c["denoise_seed"], c["denoise"]), c["tile_w"], c["tile_h"], c["padding"],
+                                    c["mask_blur"], c["uniform"])
+        ref = np.load(os.path.join(G, f"single_{c['name']}.npz"))["out"]
+        assert np.array_equal(out.cpu().numpy(), orc.dequantize_u8(ref))
+
+    cache = engine.GraphedWaves._cache
+    cache.clear()
+    run(cases[0]), run(cases[1])
+    held = list(cache.values())
+    assert len(held) == 2
+    for _ in range(3):
+        run(cases[0]), run(cases[1])
+    assert list(cache.values()) == held or list(cache.values()) == held[::-1]        # same objects: nothing was recaptured
+    first = held[0]
+    for i in range(cache.capacity - 1):                                              # fill the cache with other geometries
+        x = torch.rand(1, 96 + 8 * i, 128, 3, device=DEV)
+        engine.upscale_single(x, T0Denoiser(1, 0.5), 64, 64, 8, 4, True)
+        run(cases[1])                                                                # keeps this one recent
+    assert held[1] in cache.values() and first not in cache.values() and len(cache) == cache.capacity
+    run(cases[0])                                                                    # recaptured, still exact
+
+
 def test_node_rejects_bad_batch():
     node = UltimateSDUpscaleDistributed()
     with pytest.raises(ValueError, match="4n\\+1"):

@@ -304,6 +304,9 @@ def test_pinned_pool_never_recycles_a_buffer_somebody_still_sees():
     assert pool.get((4, 8)).data_ptr() != pc          # a numpy array is alive
     del n
     assert pool.get((4, 8)).data_ptr() in (pa, pc)
+    for i in range(10):                                 # many shapes: only the most recently used ones keep buffers
+        pool.get((3, 5 + i))
+    assert len(pool.bufs) == pool.bufs.capacity and ((4, 8), torch.float32) not in pool.bufs
 
 
 @pytest.mark.parametrize("W,H,tile,pad,blur,uniform", [(7680, 4320, 512, 32, 8, True), (1300, 1100, 256, 32, 16, True),

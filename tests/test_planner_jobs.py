@@ -86,6 +86,47 @@ def test_blend_records_reproduce_ordered_blend(case, src_u8, path):
     assert np.array_equal(got, want)
 
 
+def _random_geometry(seed):
+    rng = np.random.default_rng(1000 + seed)
+    tw = int(rng.choice([64, 96, 128, 192, 256]))
+    th = tw if rng.random() < 0.7 else int(rng.choice([64, 96, 128, 192, 256]))
+    return (int(rng.integers(40, 700)), int(rng.integers(40, 500)), tw, th, int(rng.choice([0, 8, 16, 32, 48])),
+            int(rng.choice([0, 1, 4, 8, 16, 32])), bool(rng.random() < 0.7), int(rng.choice([1, 1, 2])))
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_geometries_records_reproduce_the_oracle(seed):
+    """Seeded random canvases / tile sizes / paddings / blurs / uniform or not / 1-2 frames (rectangular tiles, canvases
+    smaller than a tile, ramps wider than the padding ...): the records of every kernel family the plan selects, run by
+    the numpy model, give the oracle's crops and the oracle's canvas after the ordered blend."""
+    W, H, tw, th, pad, blur, uniform, B = _random_geometry(seed)
+    p = planner.Plan.build(W, H, tw, th, pad, blur, uniform)
+    if not p.fast:
+        pytest.skip("generic kernels: covered by the structural test below and on the GPU")
+    canvas = orc.quantize_u8(make_input("noise", seed, B, H, W))
+    mw, mh, oplan = orc.make_plan(W, H, tw, th, pad, uniform)
+    ids = list(range(len(p.tiles)))
+    boffs, btotal = p.slot_offsets(ids, B)
+    src = np.random.default_rng(seed).random(btotal, dtype=np.float32)
+    pool = km.mask_pool(p)
+    want = canvas.copy()
+    for t, o in zip(oplan, boffs):
+        proc = src[o:o + B * t.ph * t.pw * 3].reshape(B, t.ph, t.pw, 3)
+        orc.blend_processed(want, proc, t, orc.tile_mask_window(W, H, t.x, t.y, mw, mh, blur, (t.x1, t.y1, t.x2, t.y2)))
+    for path in ([1, 2] if p.mma else [1]):
+        wl, offs, total = p.crop_worklist(ids, B, path)
+        out = np.full(total, -1.0, dtype=np.float32)
+        (km.run_crop_mma if path == 2 else km.run_crop)(p, canvas, wl, out)
+        for t, o in zip(oplan, offs):
+            crop = orc.extract_tile(canvas, t)
+            assert np.array_equal(out[o:o + crop.size].reshape(crop.shape), crop), (path, t.idx)
+        for src_u8 in (False, True):
+            got = canvas.copy()
+            (km.run_blend_mma if path == 2 else km.run_blend)(
+                p, got, p.blend_worklist(ids, boffs, 1 if src_u8 else 4, path, B), orc.quantize_u8(src) if src_u8 else src, pool)
+            assert np.array_equal(got, want), (path, src_u8)
+
+
 GENERIC = [(48, 64, 512, 32, 8, True), (1021, 37, 64, 8, 8, True), (33, 515, 128, 16, 255, True), (300, 260, 128, 16, 16, False),
            (2304, 96, 1152, 0, 4, True)]
 
