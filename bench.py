@@ -522,8 +522,10 @@ def main():
             d_ms = max(ms_step - ms_without, 1e-6)
             kern[name] = {"launches": n_waves, "ms": d_ms, "bytes": wl_bytes[name], "gbps": wl_bytes[name] / (d_ms * 1e-3) / 1e9,
                           "avg_us": d_ms * 1e3 / n_waves}
-        timing_note = (f"differencing: {args.steps} steps of the full wave graph vs the same graph without this kernel's "
-                       f"{n_waves} launches, CUDA events around each batch (no event nodes inside the graph)")
+        timing_note = (f"differencing: {args.steps} steps of the full wave graph (schedule {engine.SCHEDULE}) vs the same graph "
+                       f"without this kernel's launches ({n_waves} levels), CUDA events around each batch (no event nodes inside "
+                       "the graph); with the split_crop schedule the crop figure is its share of the critical path per level "
+                       "(the early jobs run beside the previous level's sampler and blend), the blend runs alone on the main stream")
     else:
         prof = engine.KernelProfile()
         engine.PROFILE = prof
@@ -685,6 +687,7 @@ def main():
                                      "exact progressive on N ranks (dist.upscale_exact: per-wave all-gather, replicated blend)" if exact
                                      else "static replay, fixed partition"),
                        "cuda_graph": bool(engine.USE_CUDA_GRAPHS and getattr(den, "cuda_graph_safe", False)),
+                       "schedule": engine.SCHEDULE if world == 1 else None,
                        "transport": stats.get("transport"),
                        "l2": "inputs larger than L2 (canvas 99.5 MB u8 + 398 MB fp32 image per step)"},
             "clocks": clk,

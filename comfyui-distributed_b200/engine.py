@@ -132,6 +132,40 @@ class DevicePlan:
             self._wl[key] = (wl,) + self._upload(wl)
         return self._wl[key]
 
+    def split_lists(self, waves: Sequence[Sequence[int]], B: int, path_crop: int, path_blend: int):
+        """Per dependency wave, the work lists of the split schedule (planner.split_level), uploaded:
+        dict(crop=(wl, items), early / late = (wl, items) or None, offs, total, crit=(wl, items), rest=(wl, items) or None),
+        or None when some wave does not run on job records."""
+        key = ("split", tuple(tuple(int(t) for t in w) for w in waves), B, path_crop, path_blend)
+        if key not in self._wl:
+            out = []
+            for k, wave in enumerate(waves):
+                offs, _ = self.plan.slot_offsets(wave, B)
+                nxt = waves[k + 1] if k + 1 < len(waves) else None
+                prev = waves[k - 1] if k else None
+                # (the crop lists decide which blend blocks are critical: both sides use the crop path of the launch)
+                cr, coffs, ctotal, late, crit, rest = self.plan.split_level(wave, offs, nxt, prev, B, path_crop)
+                if path_blend != path_crop:
+                    crit = self.plan.blend_worklist(wave, offs, 4, path_blend, B)
+                    rest = None
+                if cr.path < 1 or crit.path < 1:
+                    out = None
+                    break
+                e = {"crop": (cr, self._upload(cr)[0]), "offs": coffs, "total": ctotal, "early": None, "late": None,
+                     "crit": (crit, self._upload(crit)[0]), "rest": None}
+                full = crit if rest is None else self.plan.blend_worklist(wave, offs, 4, path_blend, B)
+                e["full"] = e["crit"] if rest is None else (full, self._upload(full)[0])
+                if late is not None and late.any() and not late.all():
+                    we, wlate = self.plan.sub_worklist(cr, ~late), self.plan.sub_worklist(cr, late)
+                    e["early"], e["late"] = (we, self._upload(we)[0]), (wlate, self._upload(wlate)[0])
+                if rest is not None and rest.n_launch > 0 and crit.n_launch > 0:
+                    e["rest"] = (rest, self._upload(rest)[0])
+                elif rest is not None and crit.n_launch <= 0:
+                    e["crit"] = (rest, self._upload(rest)[0])
+                out.append(e)
+            self._wl[key] = out
+        return self._wl[key]
+
     def level_list(self, blend_ids: Tuple[int, ...], offs: np.ndarray, crop_ids: Tuple[int, ...], B: int, share: int = 1):
         key = ("level", blend_ids, tuple(int(o) for o in offs), crop_ids, B, share)
         if key not in self._wl:
@@ -236,6 +270,11 @@ class Canvas:
             out = torch.empty(total, dtype=torch.float32, device=self.buf.device)
         elif out.numel() < total or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("crop: `out` too small or wrong dtype/device")
+        self.crop_jobs(wl, items, out)
+        return out, offs
+
+    def crop_jobs(self, wl: WorkList, items: torch.Tensor, out: torch.Tensor):
+        """One crop launch over an explicit work list (the whole wave, or one part of a split wave)."""
         p = self.plan
         _launch("crop_resize", wl.algo_bytes * self.B,
                 lambda: nat.tile_crop_resize(self.buf.data_ptr(), self.B, p.H, p.W, self.pitch,
@@ -245,7 +284,6 @@ class Canvas:
                                              (nat.FLAG_MMA_KS2 if wl.ks2 else 0), _stream_ptr()))
         self.launches += 1
         self.algo_bytes += wl.algo_bytes * self.B
-        return out, offs
 
     # K4 (tile_ops.py:310-349 after the truncating cast of single_gpu.py:60)
     def blend(self, tile_ids: Sequence[int], src: torch.Tensor, offs: np.ndarray,
@@ -261,10 +299,16 @@ class Canvas:
         src_u8 = src.dtype == torch.uint8
         wl, items, cover = self.dp.blend_list(tile_ids, offs, src_u8, self.path_blend, self.B, part,
                                               1 if part is not None else self.share)
+        self.blend_jobs(wl, items, cover, src, canvas_ptr)
+
+    def blend_jobs(self, wl: WorkList, items: torch.Tensor, cover: Optional[torch.Tensor], src: torch.Tensor,
+                   canvas_ptr: Optional[int] = None):
+        """One blend launch over an explicit work list (all blocks of the tiles, or one part of a split wave)."""
         if items.shape[0] == 0:
             return
         p = self.plan
         src = src.contiguous()
+        src_u8 = src.dtype == torch.uint8
         n_grid = wl.n_launch if wl.n_launch >= 0 else items.shape[0]
         flags = PATH_FLAGS[wl.path] | (wl.block_rows << 8) | (wl.block_cols << 16) | (nat.FLAG_MMA_KS2 if wl.ks2 else 0)
         target = self.buf.data_ptr()
@@ -417,11 +461,13 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
     return shipped
 
 
-SCHEDULE = os.environ.get("USDU_SCHEDULE", "waves")     # waves | dag
+# waves | split_crop (default: waves whose crop launches are split by what they really depend on, run_split) | split_blend | split |
+# split_crop_a | split_crop_b | dag
+SCHEDULE = os.environ.get("USDU_SCHEDULE", "split_crop")
 
 
 def use_dag(plan: Plan, order: Sequence[int]) -> bool:
-    """Level waves by default.  The tile-granular schedule (USDU_SCHEDULE=dag) shortens the critical path from 31
+    """Level waves (with split crops, run_split) by default.  The tile-granular schedule (USDU_SCHEDULE=dag) shortens the critical path from 31
     waves to 31 single-tile chains, but on B200 with a T0-cost sampler it is SLOWER (cfg2: 1.546 vs 1.346 ms,
     profiles/r02a_*): 405 graph kernel nodes on 9 streams are bound by the ~3.4 us/node launch rate of the graph,
     not by the chain.  It pays only when the sampler call is long enough to hide node launches but too small to
@@ -474,6 +520,106 @@ def run_dag(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, lanes: Lis
         main.wait_stream(lanes[ln])
 
 
+def use_split(canvas: Canvas, order: Sequence[int]) -> bool:
+    """USDU_SCHEDULE=split*: level waves whose crop (and blend) launches are split by what the NEXT level really needs."""
+    return SCHEDULE.startswith("split") and not FUSE_LEVELS and canvas.path_crop >= 1 and canvas.path_blend >= 1 and len(canvas.plan.waves(order)) > 2
+
+
+def run_split(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, s_rest: "torch.cuda.Stream",
+              s_early: "torch.cuda.Stream", skip: Sequence[str] = ()) -> bool:
+    """run_progressive(order) with every level's two launches split by dependency (planner.split_level); meant to be
+    stream-captured.  single_gpu.py:40-64 orders a crop only after the blends that CHANGE pixels it reads:
+      * crop(k+1) = `late` jobs (their staged rectangle meets a feather support of wave k) + `early` jobs, which run on
+        `s_early` beside sampler(k) / blend(k);
+      * blend(k)  = `crit` blocks (read by a late crop job of wave k+1) + `rest`, which runs on `s_rest` beside crop_late(k+1)
+        and sampler(k+1) and only has to land before blend(k+1) and crop_early(k+2).
+    The chain per level shrinks to crop_late -> sampler -> blend_crit (about a quarter of the crop jobs and a third of the
+    blend blocks on cfg2).  Blocks are owned by one blend launch at a time (a blend rewrites whole blocks), two launches
+    that run side by side never write the same block, and a crop beside a blend only ever reads bytes whose value the
+    blend leaves as it is.  False (nothing launched) when a wave has no job-record lists.
+    SCHEDULE: "split_crop" (default) splits only the crops -- measured on cfg2: 1.129 ms against 1.177 ms for plain waves;
+    "split_blend" 1.210 ms, "split" (both) 1.270 ms: the blend's join costs more than its shorter chain saves
+    (profiles/r02w_*).  skip: bench.py's differencing measurement -- the same schedule minus one kernel kind."""
+    plan, B = canvas.plan, canvas.B
+    waves = [_sorted_by_shape(plan, w) for w in plan.waves(order)]
+    lists = canvas.dp.split_lists(waves, B, canvas.path_crop, canvas.path_blend)
+    if lists is None:
+        return False
+    dev = canvas.buf.device
+    main = torch.cuda.current_stream(dev)
+
+    def event(stream):
+        e = torch.cuda.Event()
+        e.record(stream)
+        return e
+
+    split_crop, split_blend = SCHEDULE != "split_blend", not SCHEDULE.startswith("split_crop")
+    # where the early crops of wave k+1 fork off: 0 = right after blend(k-1), 1 = after crop_late(k), 2 = after sampler(k)
+    # (with a split blend they must wait for blend_rest(k-1): 2)
+    fork_at = {"split_crop_a": 0, "split_crop_b": 1}.get(SCHEDULE, 2)
+    no_crop, no_blend = "crop" in skip, "blend" in skip
+    if not split_crop or no_crop:
+        lists = [dict(e, early=None, late=None) for e in lists]
+    if not split_blend:
+        lists = [dict(e, crit=e["full"], rest=None) for e in lists]
+    bufs = [None] * len(waves)
+    early_done = [None] * len(waves)
+    rest_done = None
+    keep = []                                     # tensors another stream still reads: released at the joins
+    new_buf = torch.zeros if no_crop else torch.empty
+    bufs[0] = new_buf(lists[0]["total"], dtype=torch.float32, device=dev)
+
+    def fork_early(k):                            # the crop jobs of wave k+1 that do not read what wave k changes
+        if k + 1 < len(waves):
+            N = lists[k + 1]
+            bufs[k + 1] = new_buf(N["total"], dtype=torch.float32, device=dev)
+            if N["early"] is not None:
+                s_early.wait_event(event(main))
+                with torch.cuda.stream(s_early):
+                    canvas.crop_jobs(N["early"][0], N["early"][1], bufs[k + 1])
+                    early_done[k + 1] = event(s_early)
+
+    for k, wave in enumerate(waves):
+        L = lists[k]
+        if fork_at == 0:
+            fork_early(k)
+        buf, offs = bufs[k], L["offs"]
+        if L["late"] is not None and early_done[k] is not None:
+            canvas.crop_jobs(L["late"][0], L["late"][1], buf)
+            if fork_at == 1:
+                fork_early(k)
+            main.wait_event(early_done[k])
+        else:
+            if not no_crop:
+                canvas.crop_jobs(L["crop"][0], L["crop"][1], buf)
+            if fork_at == 1:
+                fork_early(k)
+        out = denoise_packed(plan, wave, buf, offs, B, denoiser)
+        if L["rest"] is not None and not no_blend:    # the blocks no crop of the next wave waits for: beside the next level
+            s_rest.wait_event(event(main))
+            with torch.cuda.stream(s_rest):
+                canvas.blend_jobs(L["rest"][0], L["rest"][1], None, out)
+                this_rest = event(s_rest)
+        else:
+            this_rest = None
+        if rest_done is not None:                 # blend_rest(k-1) has landed: blocks change hands, early crops may read them
+            main.wait_event(rest_done)
+            keep.clear()
+        if this_rest is not None:
+            keep.append(out)                      # blend_rest(k) reads it on the other stream until the next join
+        rest_done = this_rest
+        if fork_at == 2:
+            fork_early(k)
+        if not no_blend:
+            canvas.blend_jobs(L["crit"][0], L["crit"][1], None, out)
+        bufs[k] = None
+    if rest_done is not None:
+        main.wait_event(rest_done)
+    # (every launch on the side streams is already joined through its event; a stream that never joined the capture must
+    # not be waited for)
+    return True
+
+
 class GraphedWaves:
     """The wave loop of a progressive job (crop -> sampler -> blend, x waves) captured once
     into a CUDA graph on a static canvas: one graph launch replaces ~5 kernel launches per
@@ -510,10 +656,16 @@ class GraphedWaves:
         # tile-granular DAG on several streams (no per-kernel profile, no tile dictionary: those stay wave mode)
         self.dag = bool(order) and profile is None and not keep_processed and use_dag(dp.plan, order)
         lanes = [torch.cuda.Stream(device=dp.device) for _ in range(max(dp.plan.dag(order)[0]) + 1)] if self.dag else []
+        self.split = (bool(order) and profile is None and not keep_processed and payload is None and not external_crop
+                      and use_split(self.canvas, order))
+        if self.split:
+            lanes = [torch.cuda.Stream(device=dp.device), torch.cuda.Stream(device=dp.device)]
 
         def body():
             if self.dag:
                 run_dag(self.canvas, order, denoiser, lanes, self.payload, where, skip)
+                return {}
+            if self.split and run_split(self.canvas, order, denoiser, lanes[0], lanes[1], skip):
                 return {}
             return run_progressive(self.canvas, order, denoiser, keep_processed, self.payload, where, skip, self.crop_buf)
 

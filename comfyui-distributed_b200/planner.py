@@ -609,6 +609,52 @@ class Plan:
         return WorkList(np.ascontiguousarray(items), None, pw_max, ph_max, nbytes,
                         block_rows=0 if use_fast else bh_max, block_cols=0 if use_fast else bw, path=path, ks2=ks2), offs, total
 
+    def crop_split(self, wl: WorkList, prev_ids: Sequence[int]) -> np.ndarray:
+        """late[j]: job j of a tensor-core / fast crop work list stages canvas pixels that some tile of `prev_ids` (the
+        previous dependency wave) changes -- its staged rectangle meets that tile's feather support.  The other jobs read
+        pixels whose VALUES the previous wave's blend does not touch (a blend rewrites whole blocks, but only pixels under
+        a non-zero alpha change), so they may run before or beside it (single_gpu.py:40-64 orders only what overlaps)."""
+        J = wl.items.reshape(-1, nat.JOB_WORDS).astype(np.int64)
+        x0, y0 = J[:, nat.J_SRC_A], J[:, nat.J_SRC_B]
+        x1, y1 = x0 + J[:, nat.J_LEAD] + J[:, nat.J_COLS], y0 + J[:, nat.J_ROWS]   # (integer-pipe records start `lead` pixels early)
+        late = np.zeros(J.shape[0], dtype=bool)
+        for tid in prev_ids:
+            t = self.tiles[tid]
+            sx0, sy0, sx1, sy1 = self.support(t)
+            if sx1 > sx0 and sy1 > sy0:
+                late |= (x0 < t.x1 + sx1) & (t.x1 + sx0 < x1) & (y0 < t.y1 + sy1) & (t.y1 + sy0 < y1)
+        return late
+
+    @staticmethod
+    def sub_worklist(wl: WorkList, mask: np.ndarray) -> WorkList:
+        """The jobs of an unchained job list (crop) selected by `mask`, same launch geometry."""
+        import dataclasses
+        J = wl.items.reshape(-1, nat.JOB_WORDS)
+        keep = int(mask.sum())
+        return dataclasses.replace(wl, items=np.ascontiguousarray(J[mask]), algo_bytes=int(wl.algo_bytes * keep / max(J.shape[0], 1)))
+
+    def split_level(self, wave: Sequence[int], offs: np.ndarray, nxt: Optional[Sequence[int]], prev: Optional[Sequence[int]],
+                    B: int, path: int = 2):
+        """Work lists of one dependency wave for the split schedule (engine.run_split).
+        -> (crop, offs, total, late mask or None, blend_crit, blend_rest or None).
+        crop jobs: `late` ones read pixels the previous wave `prev` changes, the rest may run beside the previous wave's
+        sampler and blends.  blend blocks: `crit` ones are read by a late crop job of the NEXT wave `nxt`, the rest only
+        has to land before the next wave's blends and the crops of the wave after it."""
+        cr, coffs, ctotal = self.crop_worklist(wave, B, path)
+        late = self.crop_split(cr, prev) if (prev and cr.path >= 1) else None
+        if not nxt:
+            return cr, coffs, ctotal, late, self.blend_worklist(wave, offs, 4, path, B), None
+        ncr, _, _ = self.crop_worklist(nxt, B, path)
+        if ncr.path < 1:
+            return cr, coffs, ctotal, late, self.blend_worklist(wave, offs, 4, path, B), None
+        nl = self.crop_split(ncr, wave)
+        J = ncr.items.reshape(-1, nat.JOB_WORDS).astype(np.int64)[nl]
+        rects = np.stack([J[:, nat.J_SRC_A], J[:, nat.J_SRC_B], J[:, nat.J_SRC_A] + J[:, nat.J_COLS],
+                          J[:, nat.J_SRC_B] + J[:, nat.J_ROWS]], 1) if J.shape[0] else np.zeros((0, 4), np.int64)
+        crit = self.blend_worklist(wave, offs, 4, path, B, blocks=(rects, True))
+        rest = self.blend_worklist(wave, offs, 4, path, B, blocks=(rects, False))
+        return cr, coffs, ctotal, late, crit, rest
+
     MAX_LEVEL_DEPS = 4
 
     def level_worklist(self, blend_ids: Sequence[int], offs: np.ndarray, crop_ids: Sequence[int], B: int, share: int = 1):
@@ -753,12 +799,14 @@ class Plan:
 
     def blend_worklist(self, tile_ids: Sequence[int], offs: np.ndarray, src_bytes_per_elem: int = 4,
                        use_fast: Optional[bool] = None, B: int = 1, part: Optional[Tuple[int, int]] = None,
-                       share: int = 1) -> WorkList:
+                       share: int = 1, blocks: Optional[Tuple[np.ndarray, bool]] = None) -> WorkList:
         """Canvas blocks touched by the given tiles; each block lists its tiles in the
         given order (the order of `tile_ids` IS the blend order).  part = (i, n): only the blocks of the i-th of n
         horizontal slabs of the canvas (whole block rows, WorkList.rows = the slab's canvas rows; the n slabs tile
         the canvas) -- every block is owned by exactly one CTA, so n participants given the same tile list
-        composite disjoint slabs (dist.upscale_static: each rank finishes its own slab of the final canvas)."""
+        composite disjoint slabs (dist.upscale_static: each rank finishes its own slab of the final canvas).
+        blocks = (rects int64 [m, 4] of canvas rectangles x0, y0, x1, y1, keep): only the blocks that intersect one of the
+        rectangles (keep = True) or none of them (keep = False) -- the two launches of a split level (split_level)."""
         path = self.kernel_path(use_fast)
         use_fast = path >= 1
         ext = []
@@ -773,6 +821,14 @@ class Plan:
             i, n = part
             lo_b, hi_b = (nby * i) // n, (nby * (i + 1)) // n
             rows = (min(lo_b * bh, self.H), min(hi_b * bh, self.H))
+        sel = None
+        if blocks is not None:
+            rects, keep = blocks
+            hit = np.zeros((nby, nbx), dtype=bool)
+            for rx0, ry0, rx1, ry1 in np.asarray(rects, dtype=np.int64).reshape(-1, 4).tolist():
+                if rx1 > rx0 and ry1 > ry0:
+                    hit[max(ry0, 0) // bh: (min(ry1, self.H) - 1) // bh + 1, max(rx0, 0) // bw: (min(rx1, self.W) - 1) // bw + 1] = True
+            sel = (hit if keep else ~hit).ravel()
         keys, tids, seq = [], [], []
         pw_max = ph_max = 1
         nbytes = 0
@@ -789,12 +845,17 @@ class Plan:
                 if gy.size == 0:
                     continue
             k = (gy[:, None] * nbx + gx[None, :]).ravel()
+            n_all = k.size
+            if sel is not None:
+                k = k[sel[k]]
+                if k.size == 0:
+                    continue
             keys.append(k)
             tids.append(np.full(k.size, tid, dtype=np.int64))
             seq.append(np.full(k.size, s, dtype=np.int64))
             pw_max = max(pw_max, self._span_max(t.pw, t.ew, bw, False))
             ph_max = max(ph_max, self._span_max(t.ph, t.eh, bh, False))
-            frac = 1.0 if part is None else gy.size * bh / max(Y1 - Y0, 1)
+            frac = (1.0 if part is None else gy.size * bh / max(Y1 - Y0, 1)) * (k.size / max(n_all, 1))
             nbytes += int(min(frac, 1.0) * (t.pw * t.ph * 3 * src_bytes_per_elem + 2 * (sx1 - sx0) * (sy1 - sy0) * 3))
         if not keys:
             return WorkList(np.zeros((0, nat.JOB_WORDS if use_fast else nat.BLEND_ITEM_WORDS), np.int32),

@@ -86,3 +86,29 @@ def test_fused_level_launches_give_the_same_canvas():
         assert _digest(out) == want
     finally:
         engine.FUSE_LEVELS = False
+
+
+@pytest.mark.parametrize("name,schedule", [("cfg2_4k_to_8k_sdxl_512px", "split_crop"), ("cfg2_4k_to_8k_sdxl_512px", "split"),
+                                           ("cfg2_4k_to_8k_sdxl_512px", "split_blend"), ("cfg2_4k_to_8k_sdxl_512px", "split_crop_a"),
+                                           ("cfg2_4k_to_8k_sdxl_512px", "waves"), ("cfg5_video_17f_4k", "split"),
+                                           ("cfg5_video_17f_4k", "waves"), ("cfg1_512_256px", "split")])
+def test_every_level_schedule_gives_the_same_canvas(name, schedule):
+    """engine.SCHEDULE: "split_crop" is the default (engine.run_split: the crop jobs of wave k+1 that do not read what wave
+    k changes run on a second stream beside sampler(k) / blend(k)); "split" also splits the blends (crit / rest, three
+    streams), "split_blend" only those, "split_crop_a" forks the early crops one step earlier, "waves" is the plain level
+    loop -- the same digest as the reference on every replay of every one of them."""
+    B, H, W, tile, pad, blur = WORKLOADS[name]
+    want = _expected(name)
+    img = _canvas(B, H, W).cuda()
+    saved = engine.SCHEDULE
+    engine.SCHEDULE = schedule
+    try:
+        for _ in range(3):
+            out = engine.upscale_single(img, T0Denoiser(123, 0.5), tile, tile, pad, blur, True)
+            assert _digest(out) == want
+            del out
+        if name != "cfg1_512_256px":                    # (cfg1 has 4 single-tile waves: run_split has nothing to split)
+            gw = list(engine.GraphedWaves._cache.values())[-1]
+            assert gw.split == schedule.startswith("split")
+    finally:
+        engine.SCHEDULE = saved
