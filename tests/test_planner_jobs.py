@@ -229,18 +229,20 @@ def test_level_worklists_order_every_crop_after_the_blends_it_reads(W, H, tile, 
     assert checked > 0
 
 
-@pytest.mark.parametrize("W,H,tile,pad,blur,B,extreme", [
-    (1100, 900, 256, 32, 16, 1, "rest_last_early_first"), (700, 560, 128, 16, 8, 2, "rest_last_early_first"),
-    (700, 560, 128, 16, 8, 2, "rest_first_early_last")])          # (2300 x 1500 / 512, both orders: checked once, 3 min)
-def test_split_levels_give_the_sequential_result_in_every_legal_order(W, H, tile, pad, blur, B, extreme):
+@pytest.mark.parametrize("W,H,tile,pad,blur,B,extreme,path", [
+    (1100, 900, 256, 32, 16, 1, "rest_last_early_first", 2), (700, 560, 128, 16, 8, 2, "rest_last_early_first", 2),
+    (700, 560, 128, 16, 8, 2, "rest_first_early_last", 2), (640, 512, 128, 16, 8, 1, "rest_last_early_first", 1)])
+#   (2300 x 1500 / 512, both orders: checked once, 3 min)
+def test_split_levels_give_the_sequential_result_in_every_legal_order(W, H, tile, pad, blur, B, extreme, path):
     """engine.run_split launches, per dependency wave, crop_early / crop_late and blend_crit / blend_rest
     (planner.split_level) on three streams.  The numpy model executes the same lists SEQUENTIALLY in the two extreme
     interleavings the stream dependencies allow -- the early crops of wave k+1 before ANY blend of wave k and
     blend_rest(k) after the sampler of wave k+1, or the other way round -- and must reproduce the oracle's
     process_single (tile after tile) bit for bit: the split only reorders work that does not interact."""
     p = planner.Plan.build(W, H, tile, tile, pad, blur, True)
-    if not p.mma:
-        pytest.skip("no tensor-core path")
+    if not (p.mma if path == 2 else p.fast):
+        pytest.skip("no job-record path")
+    run_crop, run_blend = (km.run_crop_mma, km.run_blend_mma) if path == 2 else (km.run_crop, km.run_blend)
     img = make_input("noise", 3, B, H, W)
     den = orc.make_t0_denoiser(5, 0.5)
     want = orc.process_single(img, den, tile, tile, pad, blur, True)
@@ -253,13 +255,13 @@ def test_split_levels_give_the_sequential_result_in_every_legal_order(W, H, tile
     for k, w in enumerate(waves):
         offs, _ = p.slot_offsets(w, B)
         cr, coffs, ctotal, late, crit, rest = p.split_level(w, offs, waves[k + 1] if k + 1 < len(waves) else None,
-                                                            waves[k - 1] if k else None, B, 2)
+                                                            waves[k - 1] if k else None, B, path)
         assert np.array_equal(coffs, offs)
         early = lt = None
         if late is not None and late.any() and not late.all():
             early, lt = p.sub_worklist(cr, ~late), p.sub_worklist(cr, late)
         if rest is not None:                                     # the two blend launches share out the blocks of the wave
-            full = p.blend_worklist(w, offs, 4, 2, B)
+            full = p.blend_worklist(w, offs, 4, path, B)
             assert crit.n_launch + rest.n_launch == full.n_launch and crit.block_rows == rest.block_rows == full.block_rows
         L.append(dict(crop=cr, early=early, late=lt, total=ctotal, offs=offs, crit=crit, rest=rest))
     assert any(e["early"] is not None for e in L) and any(e["rest"] is not None and e["rest"].n_launch > 0 for e in L)
@@ -279,29 +281,29 @@ def test_split_levels_give_the_sequential_result_in_every_legal_order(W, H, tile
         e = L[k]
         if e["late"] is not None:
             if k in early_pending:                                # "early last": right before the sampler needs it
-                km.run_crop_mma(p, canvas, early_pending.pop(k), bufs[k])
-            km.run_crop_mma(p, canvas, e["late"], bufs[k])
+                run_crop(p, canvas, early_pending.pop(k), bufs[k])
+            run_crop(p, canvas, e["late"], bufs[k])
         else:
-            km.run_crop_mma(p, canvas, e["crop"], bufs[k])
+            run_crop(p, canvas, e["crop"], bufs[k])
         assert not (bufs[k] < 0).any()
         out = sample(k, bufs[k])
         this_rest = (e["rest"], out) if e["rest"] is not None and e["rest"].n_launch > 0 else None
         if extreme == "rest_first_early_last" and this_rest is not None:
-            km.run_blend_mma(p, canvas, this_rest[0], this_rest[1], pool)
+            run_blend(p, canvas, this_rest[0], this_rest[1], pool)
             this_rest = None
         if pending_rest is not None:                              # the join: blend_rest(k-1) at the latest here
-            km.run_blend_mma(p, canvas, pending_rest[0], pending_rest[1], pool)
+            run_blend(p, canvas, pending_rest[0], pending_rest[1], pool)
         pending_rest = this_rest
         if k + 1 < len(waves):
             bufs[k + 1] = np.full(L[k + 1]["total"], -1.0, np.float32)
             if L[k + 1]["early"] is not None:
                 if extreme == "rest_last_early_first":            # before any blend of wave k
-                    km.run_crop_mma(p, canvas, L[k + 1]["early"], bufs[k + 1])
+                    run_crop(p, canvas, L[k + 1]["early"], bufs[k + 1])
                 else:
                     early_pending[k + 1] = L[k + 1]["early"]
         if e["crit"].n_launch != 0:
-            km.run_blend_mma(p, canvas, e["crit"], out, pool)
+            run_blend(p, canvas, e["crit"], out, pool)
         del bufs[k]
     if pending_rest is not None:
-        km.run_blend_mma(p, canvas, pending_rest[0], pending_rest[1], pool)
+        run_blend(p, canvas, pending_rest[0], pending_rest[1], pool)
     assert np.array_equal(orc.dequantize_u8(canvas), want)
