@@ -464,6 +464,9 @@ def run_progressive(canvas: Canvas, order: Sequence[int], denoiser: Denoiser, ke
 # waves | split_crop (default: waves whose crop launches are split by what they really depend on, run_split) | split_blend | split |
 # split_crop_a | split_crop_b | dag
 SCHEDULE = os.environ.get("USDU_SCHEDULE", "split_crop")
+SCHEDULES = ("waves", "split_crop", "split_crop_a", "split_crop_b", "split_blend", "split", "dag")
+if SCHEDULE not in SCHEDULES:
+    raise ValueError(f"USDU_SCHEDULE={SCHEDULE!r}: expected one of {', '.join(SCHEDULES)}")
 
 
 def use_dag(plan: Plan, order: Sequence[int]) -> bool:
